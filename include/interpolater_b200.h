@@ -1,0 +1,118 @@
+/*
+ * interpolater_b200 — C ABI of the B200-native IDW / Cressman engine.
+ *
+ * This is the drop-in boundary for InterpolateR's data-parallel hot path.  The reference is pure
+ * R and has NO FFI today (NAMESPACE has no useDynLib, there is no src/); the seam is created by
+ * replacing two R code regions with one .Call each:
+ *
+ *   ipr_idw_f64       replaces  R/IDW.R:249-355       (grid_xy -> dist_mat -> w_base ->
+ *                                                      pblapply(call_idw) -> list of rasters)
+ *   ipr_cressman_f64  replaces  R/Cressman.R:268-345  (dist_mat -> weights_list ->
+ *                                                      pblapply(call_crsm_opt) -> per-radius stacks)
+ *
+ * Plain pointers and sizes only; no torch / R / C++ types cross the boundary.  All matrices are
+ * column-major doubles exactly as R stores them.  Missing values on input are any NaN (R's
+ * is.na() is TRUE for NA_real_ and NaN); missing values on output are written with R's
+ * NA_real_ bit pattern 0x7FF00000000007A2.
+ *
+ * Every entry point returns 0 on success or a negative IPR_E* code, and writes a message to
+ * `err` (if non-NULL).  There is NO CPU fallback: without a usable sm_100 device the calls fail.
+ */
+#ifndef INTERPOLATER_B200_H
+#define INTERPOLATER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPR_OK 0
+#define IPR_EINVAL (-1)   /* bad argument */
+#define IPR_ECUDA (-2)    /* CUDA runtime error / no device */
+#define IPR_ENOMEM (-3)   /* device or pinned-host allocation failed */
+#define IPR_EUNSUPPORTED (-4)
+
+/* library version: major*10000 + minor*100 + patch */
+int ipr_version(void);
+/* number of visible CUDA devices of compute capability 10.x; negative on error */
+int ipr_device_count(void);
+/* R's NA_real_ as written by the engine */
+double ipr_na_real(void);
+
+/* ---------------------------------------------------------------------------------------
+ * One-shot host-buffer entry points (what the R .Call shim binds).
+ *
+ *   cell_x, cell_y   n_cells      grid-cell centres in terra cell order (R/IDW.R:249-257)
+ *   st_x, st_y       n_st         training-station coordinates, aligned with obs columns
+ *   obs              n_dates x n_st, column-major (each station's series contiguous, as the
+ *                    columns of BD_Obs are); NaN/NA = missing
+ *   devices          n_devices CUDA ordinals (NULL / 0 => device 0); date blocks are sharded
+ *                    contiguously over them, no inter-GPU reduction
+ *   out              caller-owned, column-major n_cells x n_dates (one layer per date)
+ * ------------------------------------------------------------------------------------- */
+int ipr_idw_f64(const double* cell_x, const double* cell_y, int64_t n_cells,
+                const double* st_x, const double* st_y, int32_t n_st,
+                const double* obs, int32_t n_dates, double p,
+                const int* devices, int n_devices,
+                double* out, char* err, size_t errlen);
+
+/* radii_m: n_radii search radii in metres, ascending and unique (R/Cressman.R:216-218 does the
+ * km->m, sort(unique()) before the seam).  out: n_radii consecutive column-major
+ * n_cells x n_dates stacks (radius-major). */
+int ipr_cressman_f64(const double* cell_x, const double* cell_y, int64_t n_cells,
+                     const double* st_x, const double* st_y, int32_t n_st,
+                     const double* obs, int32_t n_dates,
+                     const double* radii_m, int32_t n_radii,
+                     const int* devices, int n_devices,
+                     double* out, char* err, size_t errlen);
+
+/* ---------------------------------------------------------------------------------------
+ * Device-resident plan API (used by the one-shot calls, the benchmark and the Python host
+ * mirror): inputs stay in HBM, outputs are written to caller-supplied DEVICE pointers.
+ * A plan is bound to one device and owns one compute stream.
+ * ------------------------------------------------------------------------------------- */
+typedef struct ipr_plan ipr_plan;
+
+int ipr_plan_create(ipr_plan** plan, int device,
+                    const double* cell_x, const double* cell_y, int64_t n_cells,
+                    const double* st_x, const double* st_y, int32_t n_st,
+                    int32_t n_dates, char* err, size_t errlen);
+void ipr_plan_destroy(ipr_plan* plan);
+
+/* H2D copy of obs (host, column-major n_dates x n_st) followed by the device-side preparation
+ * (NA -> 0 / mask split, per-date early-out flags).  Asynchronous w.r.t. the host except for a
+ * n_dates-byte flag read-back. */
+int ipr_plan_set_obs(ipr_plan* plan, const double* obs, char* err, size_t errlen);
+/* same, obs already on the device (n_dates x n_st column-major) */
+int ipr_plan_set_obs_device(ipr_plan* plan, const double* d_obs, char* err, size_t errlen);
+
+/* Interpolate dates [t0, t1) into d_out (DEVICE pointer): layer t is written at
+ * d_out + (t - t0) * ld_out, ld_out >= n_cells.  Launches are asynchronous on the plan stream. */
+int ipr_plan_idw(ipr_plan* plan, double p, int32_t t0, int32_t t1,
+                 double* d_out, int64_t ld_out, char* err, size_t errlen);
+/* radius ri's stack starts at d_out + ri * stack_stride (elements) */
+int ipr_plan_cressman(ipr_plan* plan, const double* radii_m, int32_t n_radii,
+                      int32_t t0, int32_t t1, double* d_out, int64_t ld_out,
+                      int64_t stack_stride, char* err, size_t errlen);
+
+int ipr_plan_sync(ipr_plan* plan);
+/* CUDA events on the plan's stream, for timing exactly what the plan launched */
+int ipr_plan_timer_start(ipr_plan* plan);
+int ipr_plan_timer_stop(ipr_plan* plan, float* elapsed_ms); /* synchronises */
+/* counters since plan creation: kernels launched by this library on the plan's stream */
+int64_t ipr_plan_launch_count(const ipr_plan* plan);
+/* number of (cell, station) pairs at exactly zero distance found for this geometry */
+int64_t ipr_plan_zero_pairs(const ipr_plan* plan);
+/* raw cudaStream_t of the plan (as void*) so a host framework can order its own work */
+void* ipr_plan_stream(const ipr_plan* plan);
+
+/* pinned host memory helpers for callers that want zero-copy-staging D2H (the benchmark) */
+void* ipr_host_alloc(size_t bytes);
+void ipr_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INTERPOLATER_B200_H */

@@ -1,0 +1,669 @@
+// interpolater_b200 — C ABI implementation: device-resident plan, kernel scheduling, and the
+// one-shot host-buffer entry points with the multi-GPU date-block scheduler.
+// See include/interpolater_b200.h for the contract and the reference lines each call replaces.
+#include "../../include/interpolater_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "ipr_kernels.cuh"
+
+using namespace ipr;
+
+namespace {
+
+void set_err(char* err, size_t errlen, const char* fmt, ...) {
+    if (!err || errlen == 0) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err, errlen, fmt, ap);
+    va_end(ap);
+}
+
+#define IPR_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            set_err(err, errlen, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, \
+                    __LINE__, cudaGetErrorString(e_));                                          \
+            return (e_ == cudaErrorMemoryAllocation) ? IPR_ENOMEM : IPR_ECUDA;                  \
+        }                                                                                       \
+    } while (0)
+
+inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+inline double canon_zero(double v) { return v == 0.0 ? 0.0 : v; }  // -0 -> +0
+
+}  // namespace
+
+struct ipr_plan {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long n_cells = 0, c_pad = 0;
+    int n_st = 0, s_pad = 0, n_dates = 0, ldz = 0;
+    double2* d_cell = nullptr;
+    double2* d_st = nullptr;
+    double* d_obs = nullptr;  // raw, column-major n_dates x n_st (ld = n_dates)
+    double* d_z0 = nullptr;
+    double* d_mask = nullptr;
+    uint8_t* d_flag = nullptr;
+    uint8_t* d_has_na = nullptr;
+    int* d_counters = nullptr;  // [0] zero pairs, [1] non-finite obs
+    int2* d_pairs = nullptr;
+    int pair_capacity = 0;
+    // zero-distance CSR (device) built once per geometry
+    int n_fix = 0;
+    int* d_fix_cell = nullptr;
+    int* d_fix_off = nullptr;
+    int* d_fix_st = nullptr;
+    long long zero_pairs = 0;
+    std::vector<uint8_t> h_has_na;
+    bool obs_ready = false;
+    long long launches = 0;
+};
+
+namespace {
+
+template <int NP, bool MASKED, int WMODE>
+int launch_contract(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles, char* err, size_t errlen) {
+    using L = SmemLayout<NP, MASKED>;
+    static bool configured[64] = {false};
+    auto kern = contract_kernel<NP, MASKED, WMODE>;
+    if (!configured[p->device & 63]) {
+        IPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        configured[p->device & 63] = true;
+    }
+    for (size_t i0 = 0; i0 < tiles.size(); i0 += kMaxTilesPerLaunch) {
+        const int n = (int)std::min<size_t>(kMaxTilesPerLaunch, tiles.size() - i0);
+        a.tiles.n = n;
+        for (int i = 0; i < n; i++) a.tiles.t0[i] = tiles[i0 + i];
+        dim3 grid((unsigned)(p->c_pad / kCellsPerCta), (unsigned)n);
+        kern<<<grid, kThreads, L::kTotal, p->stream>>>(a);
+        IPR_CUDA(cudaGetLastError());
+        p->launches++;
+    }
+    return IPR_OK;
+}
+
+template <int WMODE>
+int run_tiles(ipr_plan* p, ContractArgs& a, const std::vector<int>& u256, const std::vector<int>& u128,
+              const std::vector<int>& m128, char* err, size_t errlen) {
+    int rc = IPR_OK;
+    if (!u256.empty() && (rc = launch_contract<16, false, WMODE>(p, a, u256, err, errlen))) return rc;
+    if (!u128.empty() && (rc = launch_contract<8, false, WMODE>(p, a, u128, err, errlen))) return rc;
+    if (WMODE != kCressman) {
+        if (!m128.empty() && (rc = launch_contract<8, true, (WMODE == kCressman ? kIdwP2 : WMODE)>(p, a, m128, err, errlen)))
+            return rc;
+    }
+    return rc;
+}
+
+// Split [t0, t1) into date tiles.  Tiles start on multiples of 128 (absolute), except that the
+// window is first aligned down to 16; blocks of 128 dates containing any NA take the masked
+// variant (when `use_mask`), aligned unmasked pairs are merged into 256-wide tiles.
+void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, std::vector<int>& u256, std::vector<int>& u128,
+                 std::vector<int>& m128) {
+    const int start = t0 & ~15;
+    std::vector<std::pair<int, bool>> blocks;  // (start, masked)
+    for (int b = start; b < t1; b += 128) {
+        bool na = false;
+        if (use_mask) {
+            const int lo = std::max(b, t0), hi = std::min(b + 128, t1);
+            for (int t = lo; t < hi; t++) na |= (p->h_has_na[t] != 0);
+        }
+        blocks.emplace_back(b, na);
+    }
+    for (size_t i = 0; i < blocks.size();) {
+        if (blocks[i].second) {
+            m128.push_back(blocks[i].first);
+            i++;
+        } else if (i + 1 < blocks.size() && !blocks[i + 1].second) {
+            u256.push_back(blocks[i].first);
+            i += 2;
+        } else {
+            u128.push_back(blocks[i].first);
+            i++;
+        }
+    }
+}
+
+int check_range(const ipr_plan* p, int t0, int t1, const double* d_out, long long ld_out, char* err, size_t errlen) {
+    if (!p) {
+        set_err(err, errlen, "plan is NULL");
+        return IPR_EINVAL;
+    }
+    if (!p->obs_ready) {
+        set_err(err, errlen, "ipr_plan_set_obs must be called before interpolating");
+        return IPR_EINVAL;
+    }
+    if (t0 < 0 || t1 > p->n_dates || t0 > t1) {
+        set_err(err, errlen, "date range [%d, %d) outside [0, %d)", t0, t1, p->n_dates);
+        return IPR_EINVAL;
+    }
+    if (!d_out || ld_out < p->n_cells) {
+        set_err(err, errlen, "output pointer is NULL or ld_out < n_cells");
+        return IPR_EINVAL;
+    }
+    return IPR_OK;
+}
+
+int scan_zero_pairs(ipr_plan* p, char* err, size_t errlen) {
+    IPR_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(int), p->stream));
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((p->n_cells + threads - 1) / threads);
+    zero_pairs_kernel<<<blocks, threads, 0, p->stream>>>(p->d_cell, p->n_cells, p->d_st, p->n_st, p->d_pairs,
+                                                         p->pair_capacity, p->d_counters);
+    IPR_CUDA(cudaGetLastError());
+    p->launches++;
+    int n = 0;
+    IPR_CUDA(cudaMemcpyAsync(&n, p->d_counters, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    IPR_CUDA(cudaStreamSynchronize(p->stream));
+    if (n > p->pair_capacity) {
+        set_err(err, errlen, "%d zero-distance (cell, station) pairs exceed the supported %d", n, p->pair_capacity);
+        return IPR_EUNSUPPORTED;
+    }
+    p->zero_pairs = n;
+    p->n_fix = 0;
+    if (n == 0) return IPR_OK;
+    std::vector<int2> h(n);
+    IPR_CUDA(cudaMemcpy(h.data(), p->d_pairs, sizeof(int2) * n, cudaMemcpyDeviceToHost));
+    std::sort(h.begin(), h.end(), [](const int2& a, const int2& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    std::vector<int> cell, off, st;
+    for (int i = 0; i < n; i++) {
+        if (i == 0 || h[i].x != h[i - 1].x) {
+            cell.push_back(h[i].x);
+            off.push_back(i);
+        }
+        st.push_back(h[i].y);
+    }
+    off.push_back(n);
+    p->n_fix = (int)cell.size();
+    cudaFree(p->d_fix_cell);
+    cudaFree(p->d_fix_off);
+    cudaFree(p->d_fix_st);
+    p->d_fix_cell = p->d_fix_off = p->d_fix_st = nullptr;
+    IPR_CUDA(cudaMalloc(&p->d_fix_cell, sizeof(int) * cell.size()));
+    IPR_CUDA(cudaMalloc(&p->d_fix_off, sizeof(int) * off.size()));
+    IPR_CUDA(cudaMalloc(&p->d_fix_st, sizeof(int) * st.size()));
+    IPR_CUDA(cudaMemcpy(p->d_fix_cell, cell.data(), sizeof(int) * cell.size(), cudaMemcpyHostToDevice));
+    IPR_CUDA(cudaMemcpy(p->d_fix_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+    IPR_CUDA(cudaMemcpy(p->d_fix_st, st.data(), sizeof(int) * st.size(), cudaMemcpyHostToDevice));
+    return IPR_OK;
+}
+
+int prepare_obs(ipr_plan* p, char* err, size_t errlen) {
+    IPR_CUDA(cudaMemsetAsync(p->d_counters + 1, 0, sizeof(int), p->stream));
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((p->n_dates + 31) / 32));
+    prep_obs_kernel<<<grid, block, 0, p->stream>>>(p->d_obs, p->n_dates, p->n_dates, p->n_st, p->d_z0, p->d_mask,
+                                                   p->ldz, p->d_flag, p->d_has_na, p->d_counters + 1);
+    IPR_CUDA(cudaGetLastError());
+    p->launches++;
+    int bad = 0;
+    p->h_has_na.resize(p->n_dates);
+    IPR_CUDA(cudaMemcpyAsync(p->h_has_na.data(), p->d_has_na, p->n_dates, cudaMemcpyDeviceToHost, p->stream));
+    IPR_CUDA(cudaMemcpyAsync(&bad, p->d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    IPR_CUDA(cudaStreamSynchronize(p->stream));
+    if (bad) {
+        set_err(err, errlen, "obs holds %d infinite value(s); only finite observations or NA are supported", bad);
+        return IPR_EUNSUPPORTED;
+    }
+    p->obs_ready = true;
+    return IPR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ipr_version(void) { return 100; }
+
+int ipr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return IPR_ECUDA;
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ok++;
+    }
+    return ok;
+}
+
+double ipr_na_real(void) {
+    double v;
+    const unsigned long long b = kNaRealBits;
+    memcpy(&v, &b, 8);
+    return v;
+}
+
+void* ipr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+void ipr_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const double* cell_y, int64_t n_cells,
+                    const double* st_x, const double* st_y, int32_t n_st, int32_t n_dates, char* err, size_t errlen) {
+    if (!plan || !cell_x || !cell_y || !st_x || !st_y) {
+        set_err(err, errlen, "NULL argument");
+        return IPR_EINVAL;
+    }
+    if (n_cells <= 0 || n_st <= 0 || n_dates <= 0) {
+        set_err(err, errlen, "n_cells, n_st and n_dates must be positive");
+        return IPR_EINVAL;
+    }
+    if (n_cells > 2000000000LL) {
+        set_err(err, errlen, "n_cells > 2e9 is not supported");
+        return IPR_EUNSUPPORTED;
+    }
+    int ndev = 0;
+    IPR_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        set_err(err, errlen, "device %d not available (%d visible)", device, ndev);
+        return IPR_ECUDA;
+    }
+    cudaDeviceProp prop;
+    IPR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_err(err, errlen, "device %d is sm_%d%d; this engine is built for sm_100a only (no fallback)", device,
+                prop.major, prop.minor);
+        return IPR_EUNSUPPORTED;
+    }
+    IPR_CUDA(cudaSetDevice(device));
+    ipr_plan* p = new ipr_plan();
+    p->device = device;
+    p->n_cells = n_cells;
+    p->c_pad = round_up(n_cells, kCellsPerCta);
+    p->n_st = n_st;
+    p->s_pad = (int)round_up(n_st, kKT);
+    p->n_dates = n_dates;
+    p->ldz = (int)round_up(n_dates, 16) + 256;
+    p->pair_capacity = std::max(4 * n_st, 65536);
+#define PLAN_CUDA(call)                   \
+    do {                                  \
+        cudaError_t e2_ = (call);         \
+        if (e2_ != cudaSuccess) {         \
+            ipr_plan_destroy(p);          \
+            IPR_CUDA(e2_);                \
+        }                                 \
+    } while (0)
+    PLAN_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    PLAN_CUDA(cudaEventCreate(&p->ev0));
+    PLAN_CUDA(cudaEventCreate(&p->ev1));
+    PLAN_CUDA(cudaMalloc(&p->d_cell, sizeof(double2) * p->c_pad));
+    PLAN_CUDA(cudaMalloc(&p->d_st, sizeof(double2) * (p->s_pad + kKT)));
+    PLAN_CUDA(cudaMalloc(&p->d_obs, sizeof(double) * (size_t)n_dates * n_st));
+    PLAN_CUDA(cudaMalloc(&p->d_z0, sizeof(double) * (size_t)p->s_pad * p->ldz));
+    PLAN_CUDA(cudaMalloc(&p->d_mask, sizeof(double) * (size_t)p->s_pad * p->ldz));
+    PLAN_CUDA(cudaMalloc(&p->d_flag, p->ldz));
+    PLAN_CUDA(cudaMalloc(&p->d_has_na, p->ldz));
+    PLAN_CUDA(cudaMalloc(&p->d_counters, sizeof(int) * 4));
+    PLAN_CUDA(cudaMalloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
+    PLAN_CUDA(cudaMemsetAsync(p->d_z0, 0, sizeof(double) * (size_t)p->s_pad * p->ldz, p->stream));
+    PLAN_CUDA(cudaMemsetAsync(p->d_mask, 0, sizeof(double) * (size_t)p->s_pad * p->ldz, p->stream));
+    PLAN_CUDA(cudaMemsetAsync(p->d_flag, 0, p->ldz, p->stream));
+    PLAN_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(int) * 4, p->stream));
+    {
+        std::vector<double2> h(p->c_pad);
+        for (long long i = 0; i < p->c_pad; i++) {
+            const long long k = std::min<long long>(i, n_cells - 1);
+            h[i] = make_double2(canon_zero(cell_x[k]), canon_zero(cell_y[k]));
+            if (!std::isfinite(h[i].x) || !std::isfinite(h[i].y)) {
+                ipr_plan_destroy(p);
+                set_err(err, errlen, "cell coordinate %lld is not finite", k);
+                return IPR_EINVAL;
+            }
+        }
+        PLAN_CUDA(cudaMemcpyAsync(p->d_cell, h.data(), sizeof(double2) * p->c_pad, cudaMemcpyHostToDevice, p->stream));
+        std::vector<double2> hs(p->s_pad + kKT, make_double2(kPadCoord, kPadCoord));
+        for (int i = 0; i < n_st; i++) {
+            hs[i] = make_double2(canon_zero(st_x[i]), canon_zero(st_y[i]));
+            if (!std::isfinite(hs[i].x) || !std::isfinite(hs[i].y)) {
+                ipr_plan_destroy(p);
+                set_err(err, errlen, "station coordinate %d is not finite", i);
+                return IPR_EINVAL;
+            }
+        }
+        PLAN_CUDA(cudaMemcpyAsync(p->d_st, hs.data(), sizeof(double2) * hs.size(), cudaMemcpyHostToDevice, p->stream));
+        PLAN_CUDA(cudaStreamSynchronize(p->stream));  // staging vectors go out of scope
+    }
+#undef PLAN_CUDA
+    int rc = scan_zero_pairs(p, err, errlen);
+    if (rc != IPR_OK) {
+        ipr_plan_destroy(p);
+        return rc;
+    }
+    *plan = p;
+    return IPR_OK;
+}
+
+void ipr_plan_destroy(ipr_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    cudaFree(p->d_cell);
+    cudaFree(p->d_st);
+    cudaFree(p->d_obs);
+    cudaFree(p->d_z0);
+    cudaFree(p->d_mask);
+    cudaFree(p->d_flag);
+    cudaFree(p->d_has_na);
+    cudaFree(p->d_counters);
+    cudaFree(p->d_pairs);
+    cudaFree(p->d_fix_cell);
+    cudaFree(p->d_fix_off);
+    cudaFree(p->d_fix_st);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+// obs on host with an explicit leading dimension (column stride, >= n_dates): used by the
+// multi-GPU scheduler to hand each device its date block of every station's series
+static int plan_set_obs_ld(ipr_plan* p, const double* obs, long long ld, char* err, size_t errlen) {
+    if (!p || !obs) {
+        set_err(err, errlen, "NULL argument");
+        return IPR_EINVAL;
+    }
+    IPR_CUDA(cudaSetDevice(p->device));
+    IPR_CUDA(cudaMemcpy2DAsync(p->d_obs, sizeof(double) * p->n_dates, obs, sizeof(double) * ld,
+                               sizeof(double) * p->n_dates, p->n_st, cudaMemcpyHostToDevice, p->stream));
+    return prepare_obs(p, err, errlen);
+}
+
+int ipr_plan_set_obs(ipr_plan* p, const double* obs, char* err, size_t errlen) {
+    return plan_set_obs_ld(p, obs, p ? p->n_dates : 0, err, errlen);
+}
+
+int ipr_plan_set_obs_device(ipr_plan* p, const double* d_obs, char* err, size_t errlen) {
+    if (!p || !d_obs) {
+        set_err(err, errlen, "NULL argument");
+        return IPR_EINVAL;
+    }
+    IPR_CUDA(cudaSetDevice(p->device));
+    IPR_CUDA(cudaMemcpyAsync(p->d_obs, d_obs, sizeof(double) * (size_t)p->n_dates * p->n_st, cudaMemcpyDeviceToDevice,
+                             p->stream));
+    return prepare_obs(p, err, errlen);
+}
+
+int ipr_plan_idw(ipr_plan* p, double pw, int32_t t0, int32_t t1, double* d_out, int64_t ld_out, char* err,
+                 size_t errlen) {
+    int rc = check_range(p, t0, t1, d_out, ld_out, err, errlen);
+    if (rc) return rc;
+    if (!(pw > 0) || !std::isfinite(pw)) {
+        set_err(err, errlen, "p must be a positive finite number");
+        return IPR_EINVAL;
+    }
+    if (t0 == t1) return IPR_OK;
+    IPR_CUDA(cudaSetDevice(p->device));
+    ContractArgs a{};
+    a.cell_xy = p->d_cell;
+    a.st_xy = p->d_st;
+    a.z0 = p->d_z0;
+    a.mask = p->d_mask;
+    a.date_flag = p->d_flag;
+    a.out = d_out;
+    a.ld_out = ld_out;
+    a.n_cells = p->n_cells;
+    a.s_pad = p->s_pad;
+    a.ldz = p->ldz;
+    a.t_lo = t0;
+    a.t_hi = t1;
+    std::vector<int> u256, u128, m128;
+    build_tiles(p, t0, t1, true, u256, u128, m128);
+    const double half = pw / 2.0;
+    if (pw == 2.0) {
+        rc = run_tiles<kIdwP2>(p, a, u256, u128, m128, err, errlen);
+    } else if (half == std::floor(half) && half <= 16.0) {
+        a.wp.n = (int)half;
+        rc = run_tiles<kIdwEvenP>(p, a, u256, u128, m128, err, errlen);
+    } else {
+        a.wp.a = -half;
+        rc = run_tiles<kIdwGenericP>(p, a, u256, u128, m128, err, errlen);
+    }
+    if (rc) return rc;
+    if (p->n_fix > 0) {
+        dim3 grid((unsigned)((t1 - t0 + 127) / 128), (unsigned)p->n_fix);
+        idw_zero_fix_kernel<<<grid, 128, 0, p->stream>>>(p->d_fix_cell, p->d_fix_off, p->d_fix_st, p->n_fix, p->d_obs,
+                                                         p->n_dates, p->d_flag, t0, t1, d_out, ld_out);
+        IPR_CUDA(cudaGetLastError());
+        p->launches++;
+    }
+    return IPR_OK;
+}
+
+int ipr_plan_cressman(ipr_plan* p, const double* radii_m, int32_t n_radii, int32_t t0, int32_t t1, double* d_out,
+                      int64_t ld_out, int64_t stack_stride, char* err, size_t errlen) {
+    int rc = check_range(p, t0, t1, d_out, ld_out, err, errlen);
+    if (rc) return rc;
+    if (!radii_m || n_radii <= 0) {
+        set_err(err, errlen, "radii_m must hold at least one radius");
+        return IPR_EINVAL;
+    }
+    for (int i = 0; i < n_radii; i++) {
+        if (!(radii_m[i] >= 0) || !std::isfinite(radii_m[i])) {
+            set_err(err, errlen, "radius %d is not a finite non-negative number", i);
+            return IPR_EINVAL;
+        }
+    }
+    if (t0 == t1) return IPR_OK;
+    IPR_CUDA(cudaSetDevice(p->device));
+    std::vector<int> u256, u128, m128;
+    build_tiles(p, t0, t1, false, u256, u128, m128);
+    for (int ri = 0; ri < n_radii; ri++) {
+        ContractArgs a{};
+        a.cell_xy = p->d_cell;
+        a.st_xy = p->d_st;
+        a.z0 = p->d_z0;
+        a.mask = p->d_mask;
+        a.date_flag = p->d_flag;
+        a.out = d_out + (size_t)ri * stack_stride;
+        a.ld_out = ld_out;
+        a.n_cells = p->n_cells;
+        a.s_pad = p->s_pad;
+        a.ldz = p->ldz;
+        a.t_lo = t0;
+        a.t_hi = t1;
+        a.wp.a = radii_m[ri] * radii_m[ri];
+        rc = run_tiles<kCressman>(p, a, u256, u128, m128, err, errlen);
+        if (rc) return rc;
+    }
+    return IPR_OK;
+}
+
+int ipr_plan_sync(ipr_plan* p) {
+    if (!p) return IPR_EINVAL;
+    cudaSetDevice(p->device);
+    return cudaStreamSynchronize(p->stream) == cudaSuccess ? IPR_OK : IPR_ECUDA;
+}
+int ipr_plan_timer_start(ipr_plan* p) {
+    if (!p) return IPR_EINVAL;
+    cudaSetDevice(p->device);
+    return cudaEventRecord(p->ev0, p->stream) == cudaSuccess ? IPR_OK : IPR_ECUDA;
+}
+int ipr_plan_timer_stop(ipr_plan* p, float* ms) {
+    if (!p || !ms) return IPR_EINVAL;
+    cudaSetDevice(p->device);
+    if (cudaEventRecord(p->ev1, p->stream) != cudaSuccess) return IPR_ECUDA;
+    if (cudaEventSynchronize(p->ev1) != cudaSuccess) return IPR_ECUDA;
+    return cudaEventElapsedTime(ms, p->ev0, p->ev1) == cudaSuccess ? IPR_OK : IPR_ECUDA;
+}
+int64_t ipr_plan_launch_count(const ipr_plan* p) { return p ? p->launches : 0; }
+int64_t ipr_plan_zero_pairs(const ipr_plan* p) { return p ? p->zero_pairs : 0; }
+void* ipr_plan_stream(const ipr_plan* p) { return p ? (void*)p->stream : nullptr; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// One-shot host-buffer entry points: multi-GPU date-block scheduler.
+// Each device gets a contiguous date block [d0, d1) (no inter-GPU reduction); inside a
+// device the block is processed in chunks through a ring of device buffers so that the D2H copy of
+// chunk i overlaps the kernels of chunk i+1.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct HostJob {
+    const double *cell_x, *cell_y, *st_x, *st_y, *obs;
+    long long n_cells;
+    int n_st, n_dates;
+    bool cressman;
+    double p;
+    const double* radii;
+    int n_radii;
+    double* out;
+};
+
+constexpr int kRing = 3;
+
+int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, size_t errlen) {
+    if (d0 >= d1) return IPR_OK;
+    const int nd = d1 - d0;
+    ipr_plan* plan = nullptr;
+    int rc = ipr_plan_create(&plan, device, job.cell_x, job.cell_y, job.n_cells, job.st_x, job.st_y, job.n_st, nd, err,
+                             errlen);
+    if (rc) return rc;
+    struct Guard {
+        ipr_plan* p;
+        double* ring[kRing] = {nullptr, nullptr, nullptr};
+        cudaEvent_t done[kRing] = {nullptr, nullptr, nullptr}, computed[kRing] = {nullptr, nullptr, nullptr};
+        cudaStream_t copy = nullptr;
+        ~Guard() {
+            cudaSetDevice(p->device);
+            if (copy) {
+                cudaStreamSynchronize(copy);
+                cudaStreamDestroy(copy);
+            }
+            for (int i = 0; i < kRing; i++) {
+                cudaFree(ring[i]);
+                if (done[i]) cudaEventDestroy(done[i]);
+                if (computed[i]) cudaEventDestroy(computed[i]);
+            }
+            ipr_plan_destroy(p);
+        }
+    } g{plan};
+    rc = plan_set_obs_ld(plan, job.obs + d0, job.n_dates, err, errlen);
+    if (rc) return rc;
+    const int n_stacks = job.cressman ? job.n_radii : 1;
+    // chunk: up to 256 dates, bounded so that one ring slot stays <= ~2 GiB per stack set
+    long long chunk = 256;
+    const long long bytes_per_date = (long long)job.n_cells * 8 * n_stacks;
+    while (chunk > 16 && chunk * bytes_per_date > (3LL << 30)) chunk /= 2;
+    chunk = std::min<long long>(chunk, round_up(nd, 16));
+    const long long stack_stride = (long long)job.n_cells * chunk;
+    IPR_CUDA(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+    const int n_chunks = (int)((nd + chunk - 1) / chunk);
+    const int n_ring = std::min(kRing, n_chunks);
+    for (int i = 0; i < n_ring; i++) {
+        IPR_CUDA(cudaMalloc(&g.ring[i], sizeof(double) * stack_stride * n_stacks));
+        IPR_CUDA(cudaEventCreateWithFlags(&g.done[i], cudaEventDisableTiming));
+        IPR_CUDA(cudaEventCreateWithFlags(&g.computed[i], cudaEventDisableTiming));
+    }
+    for (int ci = 0; ci < n_chunks; ci++) {
+        const int slot = ci % n_ring;
+        const int t0 = (int)(ci * chunk), t1 = (int)std::min<long long>(nd, t0 + chunk);
+        if (ci >= n_ring) IPR_CUDA(cudaStreamWaitEvent(plan->stream, g.done[slot], 0));
+        if (job.cressman)
+            rc = ipr_plan_cressman(plan, job.radii, job.n_radii, t0, t1, g.ring[slot], job.n_cells, stack_stride, err,
+                                   errlen);
+        else
+            rc = ipr_plan_idw(plan, job.p, t0, t1, g.ring[slot], job.n_cells, err, errlen);
+        if (rc) return rc;
+        IPR_CUDA(cudaEventRecord(g.computed[slot], plan->stream));
+        IPR_CUDA(cudaStreamWaitEvent(g.copy, g.computed[slot], 0));
+        for (int s = 0; s < n_stacks; s++) {
+            double* dst = job.out + (size_t)s * job.n_cells * job.n_dates + (size_t)(d0 + t0) * job.n_cells;
+            IPR_CUDA(cudaMemcpyAsync(dst, g.ring[slot] + (size_t)s * stack_stride,
+                                     sizeof(double) * (size_t)job.n_cells * (t1 - t0), cudaMemcpyDeviceToHost, g.copy));
+        }
+        IPR_CUDA(cudaEventRecord(g.done[slot], g.copy));
+    }
+    IPR_CUDA(cudaStreamSynchronize(plan->stream));
+    IPR_CUDA(cudaStreamSynchronize(g.copy));
+    return IPR_OK;
+}
+
+int run_host_job(const HostJob& job, const int* devices, int n_devices, char* err, size_t errlen) {
+    if (!job.cell_x || !job.cell_y || !job.st_x || !job.st_y || !job.obs || !job.out) {
+        set_err(err, errlen, "NULL argument");
+        return IPR_EINVAL;
+    }
+    if (job.n_cells <= 0 || job.n_st <= 0 || job.n_dates <= 0) {
+        set_err(err, errlen, "n_cells, n_st and n_dates must be positive");
+        return IPR_EINVAL;
+    }
+    std::vector<int> devs;
+    if (!devices || n_devices <= 0) devs.push_back(0);
+    else devs.assign(devices, devices + n_devices);
+    const int G = (int)devs.size();
+    // pin the caller's output for asynchronous D2H unless it already is pinned; failure to pin is
+    // not an error (the copies then go through the driver's pageable path)
+    const size_t out_bytes = sizeof(double) * (size_t)job.n_cells * job.n_dates * (job.cressman ? job.n_radii : 1);
+    bool registered = false;
+    {
+        cudaPointerAttributes attr;
+        cudaError_t e = cudaPointerGetAttributes(&attr, job.out);
+        if (e != cudaSuccess) cudaGetLastError();
+        if (e != cudaSuccess || attr.type == cudaMemoryTypeUnregistered) {
+            if (cudaHostRegister(job.out, out_bytes, cudaHostRegisterPortable) == cudaSuccess) registered = true;
+            else cudaGetLastError();
+        }
+    }
+    // date blocks: multiples of 128 dates so that tiles stay aligned; remainder to the last devices
+    std::vector<int> bounds(G + 1, 0);
+    {
+        const int n_blk = (job.n_dates + 127) / 128;
+        for (int g = 0; g <= G; g++) bounds[g] = std::min<long long>(job.n_dates, (long long)n_blk * g / G * 128);
+        bounds[G] = job.n_dates;
+    }
+    std::vector<int> rcs(G, IPR_OK);
+    std::vector<std::string> errs(G, std::string(256, '\0'));
+    if (G == 1) {
+        rcs[0] = run_device_block(job, devs[0], bounds[0], bounds[1], &errs[0][0], errs[0].size());
+    } else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++)
+            th.emplace_back([&, g] { rcs[g] = run_device_block(job, devs[g], bounds[g], bounds[g + 1], &errs[g][0], errs[g].size()); });
+        for (auto& t : th) t.join();
+    }
+    if (registered) cudaHostUnregister(job.out);
+    for (int g = 0; g < G; g++)
+        if (rcs[g] != IPR_OK) {
+            set_err(err, errlen, "device %d: %s", devs[g], errs[g].c_str());
+            return rcs[g];
+        }
+    return IPR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ipr_idw_f64(const double* cell_x, const double* cell_y, int64_t n_cells, const double* st_x, const double* st_y,
+                int32_t n_st, const double* obs, int32_t n_dates, double p, const int* devices, int n_devices,
+                double* out, char* err, size_t errlen) {
+    HostJob job{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, false, p, nullptr, 0, out};
+    return run_host_job(job, devices, n_devices, err, errlen);
+}
+
+int ipr_cressman_f64(const double* cell_x, const double* cell_y, int64_t n_cells, const double* st_x,
+                     const double* st_y, int32_t n_st, const double* obs, int32_t n_dates, const double* radii_m,
+                     int32_t n_radii, const int* devices, int n_devices, double* out, char* err, size_t errlen) {
+    if (!radii_m || n_radii <= 0) {
+        set_err(err, errlen, "radii_m must hold at least one radius");
+        return IPR_EINVAL;
+    }
+    HostJob job{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, true, 2.0, radii_m, n_radii, out};
+    return run_host_job(job, devices, n_devices, err, errlen);
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+"""Array-level Python front of the CUDA engine (thin: argument marshalling only).
+
+``idw_grid`` / ``cressman_grid`` are the exact Python twins of the two one-shot C entry points the
+R ``.Call`` shim binds (host buffers in, host buffers out); ``Plan`` wraps the device-resident
+plan API used by the benchmark.  All compute happens in ``lib/libinterpolater_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+
+
+def _f64(a, name):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.ndim != 1:
+        raise ValueError(f"{name} must be one-dimensional")
+    return a
+
+
+def _obs_colmajor(obs, n_st):
+    """obs as (n_dates, n_st) -> Fortran-ordered float64 (each station's series contiguous)."""
+    obs = np.asarray(obs, dtype=np.float64)
+    if obs.ndim != 2 or obs.shape[1] != n_st:
+        raise ValueError(f"obs must have shape (n_dates, {n_st}); got {obs.shape}")
+    return np.asfortranarray(obs)
+
+
+def _devices(devices):
+    if devices is None:
+        return None, 0
+    arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+    return arr, len(devices)
+
+
+def idw_grid(cell_x, cell_y, st_x, st_y, obs, p=2.0, devices=None, out=None):
+    """IDW over every cell x date.  Returns (n_cells, n_dates) float64, Fortran order (one layer
+    per date, like the values of a terra stack); NaN (R's NA_real_ payload) where the reference
+    yields NA.  Replaces R/IDW.R:249-355."""
+    lib = _native.load()
+    cx, cy = _f64(cell_x, "cell_x"), _f64(cell_y, "cell_y")
+    sx, sy = _f64(st_x, "st_x"), _f64(st_y, "st_y")
+    if cx.shape != cy.shape or sx.shape != sy.shape:
+        raise ValueError("coordinate arrays must have matching lengths")
+    ob = _obs_colmajor(obs, sx.shape[0])
+    n_dates = ob.shape[0]
+    if out is None:
+        out = np.empty((cx.shape[0], n_dates), dtype=np.float64, order="F")
+    elif out.shape != (cx.shape[0], n_dates) or not out.flags.f_contiguous or out.dtype != np.float64:
+        raise ValueError("out must be a Fortran-ordered float64 (n_cells, n_dates) array")
+    dev, ndev = _devices(devices)
+    err = _native.errbuf()
+    rc = lib.ipr_idw_f64(cx.ctypes.data, cy.ctypes.data, cx.shape[0], sx.ctypes.data, sy.ctypes.data, sx.shape[0],
+                         ob.ctypes.data, n_dates, float(p), dev, ndev, out.ctypes.data, err, _native.ERRLEN)
+    _native.check(rc, err)
+    return out
+
+
+def cressman_grid(cell_x, cell_y, st_x, st_y, obs, radii_m, devices=None, out=None):
+    """Cressman analysis for each radius (metres, ascending unique).  Returns
+    (n_radii, n_cells, n_dates) with each [ri] Fortran-ordered.  Replaces R/Cressman.R:268-345."""
+    lib = _native.load()
+    cx, cy = _f64(cell_x, "cell_x"), _f64(cell_y, "cell_y")
+    sx, sy = _f64(st_x, "st_x"), _f64(st_y, "st_y")
+    if cx.shape != cy.shape or sx.shape != sy.shape:
+        raise ValueError("coordinate arrays must have matching lengths")
+    ob = _obs_colmajor(obs, sx.shape[0])
+    n_dates = ob.shape[0]
+    rad = _f64(radii_m, "radii_m")
+    n_cells = cx.shape[0]
+    if out is None:
+        flat = np.empty(rad.shape[0] * n_cells * n_dates, dtype=np.float64)
+    else:
+        flat = out
+        if flat.ndim != 1 or flat.shape[0] != rad.shape[0] * n_cells * n_dates or flat.dtype != np.float64:
+            raise ValueError("out must be a flat float64 array of n_radii*n_cells*n_dates elements")
+    dev, ndev = _devices(devices)
+    err = _native.errbuf()
+    rc = lib.ipr_cressman_f64(cx.ctypes.data, cy.ctypes.data, n_cells, sx.ctypes.data, sy.ctypes.data, sx.shape[0],
+                              ob.ctypes.data, n_dates, rad.ctypes.data, rad.shape[0], dev, ndev,
+                              flat.ctypes.data, err, _native.ERRLEN)
+    _native.check(rc, err)
+    # radius-major, each stack column-major (n_cells fastest): view as (n_radii, n_dates, n_cells)^T
+    return flat.reshape(rad.shape[0], n_dates, n_cells).transpose(0, 2, 1)
+
+
+class Plan:
+    """Device-resident plan (include/interpolater_b200.h, ipr_plan_*): inputs live in HBM, outputs
+    are written to caller-supplied device pointers (e.g. ``torch.Tensor.data_ptr()``)."""
+
+    def __init__(self, device, cell_x, cell_y, st_x, st_y, n_dates):
+        self._lib = _native.load()
+        cx, cy = _f64(cell_x, "cell_x"), _f64(cell_y, "cell_y")
+        sx, sy = _f64(st_x, "st_x"), _f64(st_y, "st_y")
+        self.n_cells, self.n_st, self.n_dates = cx.shape[0], sx.shape[0], int(n_dates)
+        self._h = C.c_void_p()
+        err = _native.errbuf()
+        rc = self._lib.ipr_plan_create(C.byref(self._h), int(device), cx.ctypes.data, cy.ctypes.data, self.n_cells,
+                                       sx.ctypes.data, sy.ctypes.data, self.n_st, self.n_dates, err, _native.ERRLEN)
+        _native.check(rc, err)
+
+    def close(self):
+        if self._h:
+            self._lib.ipr_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_obs(self, obs):
+        ob = _obs_colmajor(obs, self.n_st)
+        if ob.shape[0] != self.n_dates:
+            raise ValueError("obs has the wrong number of dates")
+        err = _native.errbuf()
+        _native.check(self._lib.ipr_plan_set_obs(self._h, ob.ctypes.data, err, _native.ERRLEN), err)
+
+    def set_obs_device(self, d_ptr):
+        err = _native.errbuf()
+        _native.check(self._lib.ipr_plan_set_obs_device(self._h, C.c_void_p(d_ptr), err, _native.ERRLEN), err)
+
+    def idw(self, d_out, p=2.0, t0=0, t1=None, ld_out=None):
+        t1 = self.n_dates if t1 is None else t1
+        ld_out = self.n_cells if ld_out is None else ld_out
+        err = _native.errbuf()
+        _native.check(self._lib.ipr_plan_idw(self._h, float(p), t0, t1, C.c_void_p(d_out), ld_out, err,
+                                             _native.ERRLEN), err)
+
+    def cressman(self, d_out, radii_m, t0=0, t1=None, ld_out=None, stack_stride=None):
+        t1 = self.n_dates if t1 is None else t1
+        ld_out = self.n_cells if ld_out is None else ld_out
+        stack_stride = ld_out * (t1 - t0) if stack_stride is None else stack_stride
+        rad = _f64(radii_m, "radii_m")
+        err = _native.errbuf()
+        _native.check(self._lib.ipr_plan_cressman(self._h, rad.ctypes.data, rad.shape[0], t0, t1, C.c_void_p(d_out),
+                                                  ld_out, stack_stride, err, _native.ERRLEN), err)
+
+    def sync(self):
+        if self._lib.ipr_plan_sync(self._h) != 0:
+            raise _native.NativeError(-2, "stream synchronisation failed")
+
+    def timer_start(self):
+        self._lib.ipr_plan_timer_start(self._h)
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        if self._lib.ipr_plan_timer_stop(self._h, C.byref(ms)) != 0:
+            raise _native.NativeError(-2, "timer stop failed")
+        return float(ms.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.ipr_plan_launch_count(self._h))
+
+    @property
+    def zero_pairs(self) -> int:
+        return int(self._lib.ipr_plan_zero_pairs(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.ipr_plan_stream(self._h) or 0)
