@@ -1,0 +1,15 @@
+"""Date-block sharding: every output element depends only on its own cell and date, so
+GPUs take contiguous date blocks with no exchange step.  Same rule as the C++ scheduler in
+csrc/ipr_api.cu (run_host_job): block edges on multiples of `align` dates (the kernels' 128-date
+tile) so that no tile straddles two devices."""
+from __future__ import annotations
+
+
+def date_block_bounds(n_dates: int, n_shards: int, align: int = 128):
+    """Returns n_shards+1 monotone bounds; shard g owns dates [bounds[g], bounds[g+1])."""
+    if n_dates < 0 or n_shards < 1 or align < 1:
+        raise ValueError("n_dates >= 0, n_shards >= 1, align >= 1 required")
+    n_blk = (n_dates + align - 1) // align
+    b = [min(n_dates, (n_blk * g // n_shards) * align) for g in range(n_shards + 1)]
+    b[n_shards] = n_dates
+    return b

@@ -63,8 +63,8 @@ def grid_from_extent(xmin, xmax, ymin, ymax, res_m):
 def distance_matrix(cx, cy, sx, sy):
     """terra::distance(points, points) for a projected CRS: planar sqrt(dx^2 + dy^2),
     n_cells x n_est (R/IDW.R:260-268, R/Cressman.R:279-288)."""
-    dx = cx[:, None] - sx[None, :]
-    dy = cy[:, None] - sy[None, :]
+    dx = np.asfortranarray(cx[:, None] - sx[None, :])   # column-major like an R matrix
+    dy = np.asfortranarray(cy[:, None] - sy[None, :])
     return np.sqrt(dx * dx + dy * dy)
 
 
@@ -76,71 +76,87 @@ def _is_na(v):
 # --------------------------------------------------------------------------------------
 # IDW  (R/IDW.R:249-355)
 # --------------------------------------------------------------------------------------
-def idw_reference(cx, cy, sx, sy, obs, p=2.0):
-    """obs: (n_dates, n_est) with NaN for missing.  Returns (n_cells, n_dates) float64 with NaN
-    where the reference yields NA.  Follows R/IDW.R:260-342 statement by statement."""
+def idw_setup(cx, cy, sx, sy, p=2.0):
+    """Date-independent part of IDW(): dist_mat (R/IDW.R:260-268) and w_base = dist^-p (:271-278)."""
     cx = np.asarray(cx, np.float64)
     cy = np.asarray(cy, np.float64)
     sx = np.asarray(sx, np.float64)
     sy = np.asarray(sy, np.float64)
-    obs = np.asarray(obs, np.float64)
-    n_cells = cx.shape[0]
-    n_dates = obs.shape[0]
     dist_mat = distance_matrix(cx, cy, sx, sy)                      # :260-268
     with np.errstate(divide="ignore", over="ignore"):
         w_base = np.power(dist_mat, -p)                             # :273  (d == 0 -> Inf)
-    out = np.empty((n_cells, n_dates), np.float64)
-    for t in range(n_dates):                                        # :352  pblapply over dates
-        obs_vec = obs[t]                                            # :289
-        not_na = ~_is_na(obs_vec)                                   # :290
-        if not_na.any():                                            # :294
-            if np.all(np.abs(obs_vec[not_na]) < 1e-12):             # :295-296
-                out[:, t] = 0.0                                     # :297  r_zero
-                continue
-        else:
-            out[:, t] = np.nan                                      # :301  r_na
-            continue
-        has_obs = not_na                                            # :305
-        w = w_base[:, has_obs]                                      # :306
-        o = obs_vec[has_obs]                                        # :307
-        d_sub = dist_mat[:, has_obs]
-        zero_cols = np.nonzero((d_sub == 0).sum(axis=0) > 0)[0]     # :310
-        if zero_cols.size > 0:                                      # :312
-            pred = np.full(n_cells, np.nan)                         # :313
-            hit_count = np.zeros(n_cells, np.int64)                 # :314
-            for k in zero_cols:                                     # :315
-                idx = np.nonzero(d_sub[:, k] == 0)[0]               # :316-317
-                if idx.size:                                        # :318
-                    cur = pred[idx]
-                    with np.errstate(invalid="ignore"):
-                        upd = (cur * hit_count[idx] + o[k]) / (hit_count[idx] + 1)   # :322
-                    pred[idx] = np.where(np.isnan(cur), o[k], upd)  # :319-323
-                    hit_count[idx] += 1                             # :324
-            need_idw = np.nonzero(np.isnan(pred))[0]                # :327
-            if need_idw.size:                                       # :328
-                wn = w[need_idw]
-                with np.errstate(invalid="ignore", over="ignore"):
-                    numer = wn @ o                                  # :329  dgemv
-                    denom = _row_sums_na_rm(wn)                     # :330
-                with np.errstate(invalid="ignore", divide="ignore"):
-                    vals = numer / denom                            # :331
-                vals[~np.isfinite(vals) | (denom == 0)] = np.nan    # :332
-                pred[need_idw] = vals                               # :333
-        else:
+    return dist_mat, w_base
+
+
+def idw_one_date(dist_mat, w_base, obs_vec):
+    """idw_predict(data_obs) for one date (R/IDW.R:288-342), statement by statement.
+    Returns the n_cells vector of the date's layer (NaN where the reference yields NA)."""
+    n_cells = dist_mat.shape[0]
+    not_na = ~_is_na(obs_vec)                                       # :290
+    if not_na.any():                                                # :294
+        if np.all(np.abs(obs_vec[not_na]) < 1e-12):                 # :295-296
+            return np.zeros(n_cells)                                # :297  r_zero
+    else:
+        return np.full(n_cells, np.nan)                             # :301  r_na
+    has_obs = not_na                                                # :305
+    w = w_base[:, has_obs]                                          # :306
+    o = obs_vec[has_obs]                                            # :307
+    d_sub = dist_mat[:, has_obs]
+    zero_cols = np.nonzero((d_sub == 0).sum(axis=0) > 0)[0]         # :310
+    if zero_cols.size > 0:                                          # :312
+        pred = np.full(n_cells, np.nan)                             # :313
+        hit_count = np.zeros(n_cells, np.int64)                     # :314
+        for k in zero_cols:                                         # :315
+            idx = np.nonzero(d_sub[:, k] == 0)[0]                   # :316-317
+            if idx.size:                                            # :318
+                cur = pred[idx]
+                with np.errstate(invalid="ignore"):
+                    upd = (cur * hit_count[idx] + o[k]) / (hit_count[idx] + 1)   # :322
+                pred[idx] = np.where(np.isnan(cur), o[k], upd)      # :319-323
+                hit_count[idx] += 1                                 # :324
+        need_idw = np.nonzero(np.isnan(pred))[0]                    # :327
+        if need_idw.size:                                           # :328
+            wn = w[need_idw]
             with np.errstate(invalid="ignore", over="ignore"):
-                numer = w @ o                                       # :336
-                denom = _row_sums_na_rm(w)                          # :337
+                numer = wn @ o                                      # :329  dgemv
+                denom = _row_sums_na_rm(wn)                         # :330
             with np.errstate(invalid="ignore", divide="ignore"):
-                pred = numer / denom                                # :338
-            pred[~np.isfinite(pred) | (denom == 0)] = np.nan        # :339
-        out[:, t] = pred
+                vals = numer / denom                                # :331
+            vals[~np.isfinite(vals) | (denom == 0)] = np.nan        # :332
+            pred[need_idw] = vals                                   # :333
+    else:
+        with np.errstate(invalid="ignore", over="ignore"):
+            numer = w @ o                                           # :336
+            denom = _row_sums_na_rm(w)                              # :337
+        with np.errstate(invalid="ignore", divide="ignore"):
+            pred = numer / denom                                    # :338
+        pred[~np.isfinite(pred) | (denom == 0)] = np.nan            # :339
+    return pred
+
+
+def idw_reference(cx, cy, sx, sy, obs, p=2.0):
+    """obs: (n_dates, n_est) with NaN for missing.  Returns (n_cells, n_dates) float64 with NaN
+    where the reference yields NA: the date loop of R/IDW.R:352 over idw_one_date."""
+    obs = np.asarray(obs, np.float64)
+    dist_mat, w_base = idw_setup(cx, cy, sx, sy, p)
+    out = np.empty((dist_mat.shape[0], obs.shape[0]), np.float64)
+    for t in range(obs.shape[0]):                                   # :352  pblapply over dates
+        out[:, t] = idw_one_date(dist_mat, w_base, obs[t])
     return out
+
+
+#: rowSums accumulates in long double in R; emulating that in NumPy costs an extra widened copy.
+#: bench.py's CPU-baseline leg sets this to False (plain float64 pairwise sums, ~1e-16 apart) so
+#: that the timed port is not slower than R's C loop would be.
+LONG_DOUBLE_ROWSUMS = True
 
 
 def _row_sums_na_rm(m):
     """rowSums(m, na.rm = TRUE): NaN/NA entries are skipped; R accumulates in long double."""
-    mm = np.where(np.isnan(m), 0.0, m)
-    return mm.astype(np.longdouble).sum(axis=1).astype(np.float64)
+    if LONG_DOUBLE_ROWSUMS:
+        mm = np.where(np.isnan(m), 0.0, m)
+        return mm.astype(np.longdouble).sum(axis=1).astype(np.float64)
+    return np.nansum(m, axis=1)
 
 
 # --------------------------------------------------------------------------------------
@@ -152,15 +168,12 @@ def cressman_radii_m(search_radius_km):
     return np.unique(r)  # ascending, de-duplicated
 
 
-def cressman_reference(cx, cy, sx, sy, obs, radii_m):
-    """Returns a list (one per radius, ascending order as given) of (n_cells, n_dates) arrays."""
+def cressman_setup(cx, cy, sx, sy, radii_m):
+    """Date-independent part: dist_mat, dist_sq and weights_list (R/Cressman.R:279-300)."""
     cx = np.asarray(cx, np.float64)
     cy = np.asarray(cy, np.float64)
     sx = np.asarray(sx, np.float64)
     sy = np.asarray(sy, np.float64)
-    obs = np.asarray(obs, np.float64)
-    n_cells = cx.shape[0]
-    n_dates = obs.shape[0]
     dist_mat = distance_matrix(cx, cy, sx, sy)                      # :279-287
     dist_sq = dist_mat * dist_mat                                   # :288
     weights = []
@@ -172,17 +185,32 @@ def cressman_reference(cx, cy, sx, sy, obs, radii_m):
             w = num / den                                           # :295
         w[dist_mat > R] = 0.0                                       # :296
         weights.append(w)
-    outs = [np.empty((n_cells, n_dates), np.float64) for _ in radii_m]
-    for t in range(n_dates):                                        # :340
-        obs_vec = obs[t]                                            # :311
-        for ri, w in enumerate(weights):                            # :312-313
-            with np.errstate(invalid="ignore", over="ignore"):
-                prod = w * obs_vec[None, :]                         # :314 sweep(w, 2, obs, `*`)
-            numer = _row_sums_na_rm(prod)                           # :314 rowSums(na.rm=TRUE)
-            denom = _row_sums_na_rm(w)                              # :315 (ALL stations)
-            with np.errstate(invalid="ignore", divide="ignore"):
-                o = numer / denom                                   # :316
-            o[~np.isfinite(o) | (denom == 0)] = np.nan              # :317
+    return weights
+
+
+def cressman_one_date(weights, obs_vec):
+    """crsmn_logic_opt(data_obs) (R/Cressman.R:310-321): one n_cells vector per radius."""
+    res = []
+    for w in weights:                                               # :312-313
+        with np.errstate(invalid="ignore", over="ignore"):
+            prod = w * obs_vec[None, :]                             # :314 sweep(w, 2, obs, `*`)
+        numer = _row_sums_na_rm(prod)                               # :314 rowSums(na.rm=TRUE)
+        denom = _row_sums_na_rm(w)                                  # :315 (ALL stations)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            o = numer / denom                                       # :316
+        o[~np.isfinite(o) | (denom == 0)] = np.nan                  # :317
+        res.append(o)
+    return res
+
+
+def cressman_reference(cx, cy, sx, sy, obs, radii_m):
+    """Returns a list (one per radius, ascending order as given) of (n_cells, n_dates) arrays."""
+    obs = np.asarray(obs, np.float64)
+    weights = cressman_setup(cx, cy, sx, sy, radii_m)
+    n_cells = weights[0].shape[0]
+    outs = [np.empty((n_cells, obs.shape[0]), np.float64) for _ in radii_m]
+    for t in range(obs.shape[0]):                                   # :340
+        for ri, o in enumerate(cressman_one_date(weights, obs[t])):
             outs[ri][:, t] = o
     return outs
 

@@ -1,0 +1,258 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the oracle on
+the same seeded inputs, against the committed golden fixtures, and — at BASELINE.json's full size —
+through size-independent properties.  Tolerance (SURVEY §8c / north_star): 1e-9 relative in double,
+NA positions exact, exact-zero layers bit-exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import RAIN_THRESHOLD, assert_parity
+import interpolater_b200 as ipr
+from interpolater_b200 import _native, engine, synthetic
+from oracle import reference_port as ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _require_device():
+    lib = _native.load()
+    assert lib.ipr_device_count() >= 1, "no sm_100 device: the engine has no CPU fallback"
+
+
+# ---------------------------------------------------------------- seeded parity vs the oracle
+@pytest.mark.parametrize("shape", [(64, 64, 64, 32), (5, 3, 1, 1), (1, 1, 3, 7), (33, 7, 17, 130), (30, 11, 37, 700)])
+def test_idw_matches_oracle(shape):
+    ncol, nrow, n_st, n_dates = shape
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(ncol, nrow, n_st, n_dates, na_frac=0.1 if n_st > 1 else 0.0,
+                                                   plant_zero_dist=min(3, n_st, ncol * nrow),
+                                                   all_na_dates=(3,) if n_dates > 3 else (),
+                                                   all_zero_dates=(5,) if n_dates > 5 else (), seed=shape[2])
+    got = engine.idw_grid(cx, cy, sx, sy, obs, p=2.0)
+    assert_parity(got, ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label=f"idw {shape}")
+    if n_dates > 5:
+        assert np.all(got[:, 5] == 0.0), "all-zero date must give a bit-exact zero layer"
+        assert np.all(np.isnan(got[:, 3])), "all-NA date must give an NA layer"
+
+
+def test_idw_output_na_is_r_na_real():
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(4, 4, 5, 3, all_na_dates=(1,))
+    got = engine.idw_grid(cx, cy, sx, sy, obs)
+    bits = got[:, 1].view(np.uint64)
+    assert np.all(bits == 0x7FF00000000007A2)
+
+
+@pytest.mark.parametrize("p", [1.0, 1.5, 2.0, 3.0, 4.0, 6.0])
+def test_idw_powers(p):
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(20, 13, 23, 40, na_frac=0.15, plant_zero_dist=2, seed=int(p * 10))
+    assert_parity(engine.idw_grid(cx, cy, sx, sy, obs, p=p), ref.idw_reference(cx, cy, sx, sy, obs, p), label=f"p={p}")
+
+
+def test_idw_tile_variants_mixed():
+    """NA-free 256/128-date tiles and masked 128-date tiles in one call."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(30, 11, 37, 900, plant_zero_dist=2, seed=5)
+    obs[130:140, 3] = np.nan
+    obs[600, :] = np.nan
+    obs[899, 0] = np.nan
+    assert_parity(engine.idw_grid(cx, cy, sx, sy, obs), ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="mixed tiles")
+
+
+def test_idw_colocated_stations_running_mean():
+    """Several stations on one cell centre, some NA on some dates (R/IDW.R:310-326)."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(8, 8, 12, 20, na_frac=0.3, seed=11)
+    sx[:3], sy[:3] = cx[10], cy[10]
+    sx[3], sy[3] = cx[40], cy[40]
+    obs[4, :3] = np.nan           # all co-located stations missing -> plain IDW for that cell/date
+    got = engine.idw_grid(cx, cy, sx, sy, obs)
+    assert_parity(got, ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="co-located")
+
+
+def test_idw_large_utm_coordinates_and_tiny_distances():
+    rng = np.random.default_rng(3)
+    cx, cy = synthetic.regular_grid(16, 16, res_m=25.0, xmin=706058.23, ymin=9680563.48)
+    sx = 706058.23 + rng.random(40) * 400
+    sy = 9680563.48 + rng.random(40) * 400
+    sx[0], sy[0] = cx[5] + 1e-6, cy[5]      # a micrometre away: huge but finite weight
+    obs = np.round(rng.gamma(0.8, 8.0, (12, 40)), 1)
+    assert_parity(engine.idw_grid(cx, cy, sx, sy, obs), ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="utm")
+
+
+def test_idw_signed_data_conditioned_tolerance():
+    """Signed observations cancel: judged on sum w|z| / sum w as SURVEY §8c prescribes."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(12, 12, 30, 16, seed=21)
+    rng = np.random.default_rng(21)
+    obs = obs * rng.choice([-1.0, 1.0], size=obs.shape)
+    got = engine.idw_grid(cx, cy, sx, sy, obs)
+    want = ref.idw_reference(cx, cy, sx, sy, obs, 2.0)
+    scale = ref.idw_reference(cx, cy, sx, sy, np.abs(obs), 2.0)
+    assert np.all(np.abs(got - want) <= 1e-9 * np.maximum(scale, 1e-12))
+
+
+@pytest.mark.parametrize("radii_km", [[10], [20, 10], [50, 20, 10], [3, 1.5, 40, 3]])
+def test_cressman_matches_oracle(radii_km):
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(30, 20, 41, 150, na_frac=0.1, all_na_dates=(4,), seed=len(radii_km))
+    radii = ref.cressman_radii_m(radii_km)
+    got = engine.cressman_grid(cx, cy, sx, sy, obs, radii)
+    want = ref.cressman_reference(cx, cy, sx, sy, obs, radii)
+    assert got.shape == (len(radii), cx.size, 150)
+    for i in range(len(radii)):
+        assert_parity(got[i], want[i], label=f"cressman {radii[i]}")
+    # all-NA date: 0 where any station is in range, NA elsewhere (unmasked denominator quirk)
+    big = got[-1][:, 4]
+    assert np.all((big == 0.0) | np.isnan(big))
+
+
+def test_cressman_radius_without_neighbours_is_all_na():
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(6, 6, 4, 5, seed=2)
+    got = engine.cressman_grid(cx, cy, sx + 1e6, sy, obs, np.array([1000.0]))
+    assert np.isnan(got).all()
+
+
+# ---------------------------------------------------------------- golden fixtures
+def test_synthetic_golden(synthetic_golden):
+    g = synthetic_golden
+    cx, cy, sx, sy, ob = synthetic.synthetic_case(24, 20, 40, 24, na_frac=0.1, plant_zero_dist=4, all_na_dates=(3,),
+                                                  all_zero_dates=(7,))
+    assert_parity(engine.idw_grid(cx, cy, sx, sy, ob, 2.0), g["a_idw"], label="a_idw")
+    assert_parity(engine.idw_grid(cx, cy, sx, sy, ob, 3.0), g["a_idw_p3"], label="a_idw_p3")
+    got = engine.cressman_grid(cx, cy, sx, sy, ob, ref.cressman_radii_m([2, 4, 8, 30]))
+    for i in range(4):
+        assert_parity(got[i], g["a_crs"][i], label=f"a_crs[{i}]")
+    cx, cy, sx, sy, ob = synthetic.synthetic_case(20, 9, 37, 280, plant_zero_dist=2)
+    assert_parity(engine.idw_grid(cx, cy, sx, sy, ob, 2.0), g["b_idw"], label="b_idw")
+
+
+def test_packaged_idw_cfg1(packaged, packaged_golden, capfd):
+    """BASELINE.json configs[0]: IDW on the packaged data, grid_resolution=5, p=2,
+    stat_validation='M001' — through the drop-in signature."""
+    out = ipr.IDW(packaged["BD_Obs"], packaged["BD_Coord"], packaged["shapefile"], grid_resolution=5, p=2,
+                  Mask=False, training=1, stat_validation="M001")
+    ens, val = out["Ensamble"], out["Validation"]
+    assert ens.nlyr() == 60 and ens.names[0] == "2015-01-01" and ens.names[-1] == "2015-03-01"
+    assert_parity(ens.values, packaged_golden["idw"], label="cfg1 IDW")
+    assert val["ID"].tolist() == ["M001"]
+    assert np.array_equal(val[ref.GOF_COLUMNS].to_numpy()[0], packaged_golden["idw_gof"][0])
+    err = capfd.readouterr().err
+    assert "Analysis in progress. Please wait..." in err and "Validation process in progress" in err
+
+
+def test_packaged_idw_reference_test_expectations(packaged, tmp_path, capfd, monkeypatch):
+    """tests/testthat/test-IDW.R: SpatRaster with 60 layers with/without validation; n_round; mask;
+    save_model writes <name>.nc / Model_IDW.nc and says "Model saved successfully"."""
+    monkeypatch.chdir(tmp_path)
+    out = ipr.IDW(packaged["BD_Obs"], packaged["BD_Coord"], packaged["shapefile"], grid_resolution=5, p=2, n_round=1,
+                  training=1, stat_validation="M004", Rain_threshold=RAIN_THRESHOLD)
+    assert isinstance(out["Ensamble"], ipr.SpatRaster) and out["Ensamble"].nlyr() == 60
+    assert set(out["Validation"]) == {"gof", "categorical_metrics"}
+    ens = ipr.IDW(packaged["BD_Obs"], packaged["BD_Coord"], packaged["shapefile"], grid_resolution=5, p=2, n_round=1,
+                  save_model=True)
+    assert isinstance(ens, ipr.SpatRaster) and ens.nlyr() == 60
+    v = ens.values[~np.isnan(ens.values)]
+    assert np.allclose(v * 10, np.round(v * 10), atol=1e-9)          # n_round = 1
+    assert np.isnan(ens.values).any()                                 # masked by the polygon
+    assert os.path.exists("Model_IDW.nc")
+    ipr.IDW(packaged["BD_Obs"], packaged["BD_Coord"], packaged["shapefile"], grid_resolution=5, save_model=True,
+            name_save="custom")
+    assert os.path.exists("custom.nc")
+    err = capfd.readouterr().err
+    assert "Model saved successfully" in err and "Training not specified; using all data for training." in err
+
+
+def test_packaged_cressman_cfg2(packaged, packaged_golden, tmp_path, monkeypatch, capfd):
+    """BASELINE.json configs[1]: Cressman on the packaged data, search_radius=c(50,20,10)."""
+    monkeypatch.chdir(tmp_path)
+    out = ipr.Cressman(packaged["BD_Obs"], packaged["BD_Coord"], packaged["shapefile"], grid_resolution=5,
+                       search_radius=[50, 20, 10], stat_validation="M001", Rain_threshold=RAIN_THRESHOLD,
+                       save_model=True)
+    ens, val = out["Ensamble"], out["Validation"]
+    assert list(ens) == ["10 km", "20 km", "50 km"] == list(val)
+    for i, nm in enumerate(ens):
+        assert ens[nm].nlyr() == 60
+        assert_parity(ens[nm].values, packaged_golden["cressman"][i], label=f"cfg2 {nm}")
+        assert np.array_equal(val[nm]["gof"][ref.GOF_COLUMNS].to_numpy()[0], packaged_golden["cressman_gof"][i, 0])
+        assert os.path.exists(f"Radius_{nm}.nc")
+    assert "Model saved successfully" in capfd.readouterr().err
+    # tests/testthat/test-Cressman.R:38-59: random split + n_round
+    out = ipr.Cressman(packaged["BD_Obs"], packaged["BD_Coord"], packaged["shapefile"], grid_resolution=5,
+                       search_radius=10, training=0.8, n_round=2)
+    assert out["Ensamble"]["10 km"].nlyr() == 60 and out["Validation"]["10 km"]["ID"].tolist() == ["M004", "M005"]
+
+
+# ---------------------------------------------------------------- plan API / sharding / errors
+def test_plan_api_equals_one_shot_and_date_shards_agree():
+    import torch
+
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(40, 25, 50, 520, na_frac=0.02, plant_zero_dist=2, seed=9)
+    ref_out = engine.idw_grid(cx, cy, sx, sy, obs)
+    plan = engine.Plan(0, cx, cy, sx, sy, 520)
+    plan.set_obs(obs)
+    out = torch.full((520, cx.size), -1.0, dtype=torch.float64, device="cuda")
+    plan.idw(out.data_ptr(), 2.0)
+    plan.sync()
+    assert np.array_equal(out.cpu().numpy().T, ref_out, equal_nan=True)
+    # arbitrary, tile-unaligned date windows give identical values
+    out2 = torch.full((520, cx.size), -1.0, dtype=torch.float64, device="cuda")
+    for lo, hi in [(0, 7), (7, 301), (301, 520)]:
+        plan.idw(out2[lo:].data_ptr(), 2.0, t0=lo, t1=hi)
+    plan.sync()
+    assert np.array_equal(out2.cpu().numpy().T, ref_out, equal_nan=True)
+    assert plan.zero_pairs == 2 and plan.launch_count > 0
+    plan.close()
+    if torch.cuda.device_count() >= 2:
+        multi = engine.idw_grid(cx, cy, sx, sy, obs, devices=[0, 1])
+        assert np.array_equal(multi, ref_out, equal_nan=True)
+
+
+def test_error_paths_report_messages():
+    lib = _native.load()
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(4, 4, 5, 3)
+    with pytest.raises(_native.NativeError, match="p must be a positive"):
+        engine.idw_grid(cx, cy, sx, sy, obs, p=-1.0)
+    with pytest.raises(_native.NativeError, match="not available"):
+        engine.idw_grid(cx, cy, sx, sy, obs, devices=[99])
+    bad = obs.copy()
+    bad[0, 0] = np.inf
+    with pytest.raises(_native.NativeError, match="infinite"):
+        engine.idw_grid(cx, cy, sx, sy, bad)
+    err = _native.errbuf()
+    rc = lib.ipr_idw_f64(None, None, 0, None, None, 0, None, 0, 2.0, None, 0, None, err, _native.ERRLEN)
+    assert rc == -1 and b"NULL" in err.value
+
+
+# ---------------------------------------------------------------- full-size properties (cfg 3)
+def test_full_size_properties():
+    """1,000,000 cells x 2,000 stations: (i) a field that is constant over stations is reproduced
+    at every cell, (ii) linearity in the observations, (iii) min <= out <= max, (iv) a sample of
+    cells equals the oracle — checked on the device so that no 29 GB stack crosses PCIe."""
+    import torch
+
+    ncol = nrow = 1000
+    n_st, n_dates = 2000, 256
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(ncol, nrow, n_st, n_dates)
+    const = np.linspace(0.5, 40.0, n_dates)
+    z2 = np.repeat(const[:, None], n_st, axis=1)
+    plan = engine.Plan(0, cx, cy, sx, sy, n_dates)
+    out1 = torch.empty((n_dates, cx.size), dtype=torch.float64, device="cuda")
+    out2 = torch.empty_like(out1)
+    out3 = torch.empty_like(out1)
+    plan.set_obs(obs)
+    plan.idw(out1.data_ptr())
+    plan.set_obs(z2)
+    plan.idw(out2.data_ptr())
+    plan.set_obs(2.0 * obs + 3.0 * z2)
+    plan.idw(out3.data_ptr())
+    plan.sync()
+    c = torch.from_numpy(const).cuda()[:, None]
+    assert float(((out2 - c).abs() / c).max()) < 1e-12                       # (i)
+    lin = 2.0 * out1 + 3.0 * out2
+    assert float(((out3 - lin).abs() / lin.abs().clamp_min(1e-12)).max()) < 1e-9   # (ii)
+    lo = torch.from_numpy(obs.min(axis=1)).cuda()[:, None]
+    hi = torch.from_numpy(obs.max(axis=1)).cuda()[:, None]
+    assert bool(((out1 >= lo - 1e-9) & (out1 <= hi + 1e-9)).all())            # (iii)
+    idx = np.random.default_rng(0).choice(cx.size, 1500, replace=False)
+    want = ref.idw_reference(cx[idx], cy[idx], sx, sy, obs[:6], 2.0)
+    got = out1[:6][:, torch.from_numpy(idx).cuda()].cpu().numpy().T
+    assert_parity(got, want, label="full-size sample")                      # (iv)
+    plan.close()

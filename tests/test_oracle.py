@@ -1,0 +1,134 @@
+"""CPU tests of the oracle itself: pinned against the committed golden fixtures, cross-checked
+against an independent scalar restatement, and against closed-form cases."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_parity
+from interpolater_b200 import synthetic
+from oracle import reference_port as ref
+from oracle import scalar_check
+
+
+def test_packaged_grid_is_4x6(packaged):
+    bbox = packaged["raw"]["bbox"]
+    g = ref.grid_from_extent(bbox[0], bbox[1], bbox[2], bbox[3], 5000.0)
+    assert (g["ncol"], g["nrow"]) == (4, 6)
+    assert g["X"].shape == (24,)
+    # row-major from the top-left: first cell is the north-west one
+    assert g["X"][0] == pytest.approx(bbox[0] + 2500.0) and g["Y"][0] == pytest.approx(bbox[2] + 6 * 5000.0 - 2500.0)
+    assert g["Y"][0] > g["Y"][-1] and g["X"][0] < g["X"][3]
+
+
+def test_oracle_reproduces_packaged_golden(packaged, packaged_golden):
+    z, g = packaged["raw"], packaged_golden
+    stations = [str(s) for s in z["stations"]]
+    cod = [str(c) for c in z["cod"]]
+    xy = {c: (x, y) for c, x, y in zip(cod, z["X"], z["Y"])}
+    col = {s: i for i, s in enumerate(stations)}
+    train, test = ref.select_manual(stations, "M001")
+    tr = sorted(train)
+    idw = ref.idw_reference(g["grid_X"], g["grid_Y"], np.array([xy[c][0] for c in tr]), np.array([xy[c][1] for c in tr]),
+                            z["obs"][:, [col[c] for c in tr]], 2.0)
+    assert_parity(idw, g["idw"], tol=1e-13, label="cfg1 IDW")
+    crs = ref.cressman_reference(g["grid_X"], g["grid_Y"], np.array([xy[c][0] for c in train]),
+                                 np.array([xy[c][1] for c in train]), z["obs"][:, [col[c] for c in train]], g["radii_m"])
+    for i in range(3):
+        assert_parity(crs[i], g["cressman"][i], tol=1e-13, label=f"cfg2 Cressman {i}")
+
+
+def test_packaged_fixture_facts(packaged):
+    """60 dates x 10 stations, 8 NA cells (M003:2, M004:2, M007:1, M009:3), max 36.7."""
+    obs = packaged["raw"]["obs"]
+    assert obs.shape == (60, 10)
+    na = np.isnan(obs).sum(axis=0)
+    assert na.tolist() == [0, 0, 2, 2, 0, 0, 1, 0, 3, 0]
+    assert np.nanmax(obs) == pytest.approx(36.7)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/data/BD_Obs.rda"), reason="reference not mounted")
+def test_rdx3_decoder_matches_frozen_inputs(packaged):
+    from oracle import rdata
+
+    df = rdata.data_frame(rdata.load_rda("/root/reference/data/BD_Obs.rda")["BD_Obs"])
+    for i, s in enumerate(packaged["stations"]):
+        a, b = df[s], packaged["raw"]["obs"][:, i]
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+    assert df["Date::class"] == ["Date"] and df["Date"][0] == 16436.0  # 2015-01-01
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_idw_oracle_vs_scalar_restatement(seed):
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(7, 5, 9, 10, na_frac=0.2, plant_zero_dist=3, all_na_dates=(2,),
+                                                   all_zero_dates=(4,), seed=seed)
+    sx[1], sy[1] = sx[0], sy[0]  # two stations co-located on the same cell centre -> running mean
+    for p in (2.0, 1.0, 3.5):
+        a = ref.idw_reference(cx, cy, sx, sy, obs, p)
+        b = np.array(scalar_check.idw_scalar(cx.tolist(), cy.tolist(), sx.tolist(), sy.tolist(), obs.tolist(), p))
+        assert_parity(a, b, tol=1e-12, label=f"idw p={p}")
+    assert np.all(a[:, 4] == 0.0) and np.all(np.isnan(a[:, 2]))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_cressman_oracle_vs_scalar_restatement(seed):
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(7, 5, 9, 8, na_frac=0.3, all_na_dates=(1,), seed=seed)
+    radii = ref.cressman_radii_m([3, 1, 3, 0.4])
+    assert radii.tolist() == [400.0, 1000.0, 3000.0]  # sort(unique()), R/Cressman.R:217-218
+    a = ref.cressman_reference(cx, cy, sx, sy, obs, radii)
+    b = scalar_check.cressman_scalar(cx.tolist(), cy.tolist(), sx.tolist(), sy.tolist(), obs.tolist(), radii.tolist())
+    for i in range(len(radii)):
+        assert_parity(a[i], np.array(b[i]), tol=1e-12, label=f"cressman {i}")
+    # quirk: an all-NA date gives 0 (not NA) wherever a station is in range (R/Cressman.R:314-317)
+    in_range = ~np.isnan(a[2][:, 0])
+    assert np.all(a[2][in_range, 1] == 0.0)
+
+
+def test_cressman_unmasked_denominator_pulls_towards_zero():
+    """R/Cressman.R:315: the denominator keeps the weight of stations that are NA on the date."""
+    cx, cy = np.array([0.0]), np.array([0.0])
+    sx, sy = np.array([100.0, -100.0]), np.array([0.0, 0.0])
+    obs = np.array([[10.0, 10.0], [10.0, np.nan]])
+    out = ref.cressman_reference(cx, cy, sx, sy, obs, np.array([1000.0]))[0]
+    assert out[0, 0] == pytest.approx(10.0)
+    assert out[0, 1] == pytest.approx(5.0)   # not 10: the NA station still weighs in the denominator
+
+
+def test_radius_names():
+    assert ref.radius_names(np.array([10000.0, 2500.0, 50000.0])) == ["10 km", "2.5 km", "50 km"]
+
+
+def test_r_round():
+    assert ref.r_round(0.125, 2) == 0.12      # tie -> even candidate
+    assert ref.r_round(0.135, 2) == 0.14      # 0.135 is above the tie in binary
+    assert ref.r_round(2.675, 2) == 2.67      # stored as 2.67499999...
+    assert ref.r_round(-1.005, 2) == -1.0
+    assert ref.r_round(1.0, 2) == 1.0
+    assert math.isnan(ref.r_round(float("nan"), 2))
+
+
+def test_gof_closed_form():
+    obs = np.array([1.0, 2.0, 3.0, 4.0, np.nan])
+    sim = np.array([1.5, 2.5, 2.5, 5.0, 9.0])
+    g = ref.gof(sim, obs)
+    assert g["MAE"] == pytest.approx(0.625)
+    assert g["MSE"] == pytest.approx((0.25 * 3 + 1.0) / 4)
+    assert g["RMSE"] == pytest.approx(math.sqrt(0.4375))
+    assert g["PBIAS %"] == pytest.approx(100 * 1.5 / 10)
+    assert g["NSE"] == pytest.approx(1 - 1.75 / 5.0)
+    assert g["R2"] == pytest.approx(g["NSE"])
+    assert g["rPearson"] == pytest.approx(np.corrcoef(obs[:4], sim[:4])[0, 1])
+    assert g["rSpearman"] == pytest.approx(0.9486832980505138)  # ranks (1,2,3,4) vs (1,2.5,2.5,4)
+    r = g["rPearson"]
+    alpha = np.std(sim[:4], ddof=1) / np.std(obs[:4], ddof=1)
+    beta = sim[:4].mean() / 2.5
+    assert g["KGE"] == pytest.approx(1 - math.sqrt((r - 1) ** 2 + (alpha - 1) ** 2 + (beta - 1) ** 2))
+    empty = ref.gof(np.array([np.nan]), np.array([1.0]))
+    assert all(math.isnan(v) for v in empty.values())
+
+
+def test_extract_cells_edges():
+    g = ref.grid_from_extent(0.0, 40.0, 0.0, 30.0, 10.0)
+    cells = ref.extract_cells(g, [5.0, 40.0, 0.0, 41.0, 15.0], [25.0, 0.0, 30.0, 5.0, -1.0])
+    assert cells == [0, 11, 0, -1, -1]
