@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -37,6 +38,15 @@ void set_err(char* err, size_t errlen, const char* fmt, ...) {
     } while (0)
 
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+// start-up de-phasing of the two warps per SM sub-partition (cycles); tunable for experiments
+inline int stagger_cycles() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IPR_STAGGER_CYCLES");
+        v = e ? atoi(e) : 1800;
+    }
+    return v;
+}
 inline double canon_zero(double v) { return v == 0.0 ? 0.0 : v; }  // -0 -> +0
 
 }  // namespace
@@ -46,7 +56,8 @@ struct ipr_plan {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long n_cells = 0, c_pad = 0;
-    int n_st = 0, s_pad = 0, n_dates = 0, ldz = 0;
+    int n_st = 0, s_pad = 0, n_dates = 0, n_gran = 0, n_stages = 0;
+    size_t z_doubles = 0;  // size of the granule-block arrays
     double2* d_cell = nullptr;
     double2* d_st = nullptr;
     double* d_obs = nullptr;  // raw, column-major n_dates x n_st (ld = n_dates)
@@ -91,6 +102,19 @@ int launch_contract(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles,
     return IPR_OK;
 }
 
+template <int DBG>
+int launch_debug(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles, char* err, size_t errlen) {
+    using L = SmemLayout<16, false>;
+    auto kern = contract_kernel<16, false, kIdwP2, DBG>;
+    IPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    a.tiles.n = (int)tiles.size();
+    for (size_t i = 0; i < tiles.size(); i++) a.tiles.t0[i] = tiles[i];
+    dim3 grid((unsigned)(p->c_pad / kCellsPerCta), (unsigned)tiles.size());
+    kern<<<grid, kThreads, L::kTotal, p->stream>>>(a);
+    IPR_CUDA(cudaGetLastError());
+    return IPR_OK;
+}
+
 template <int WMODE>
 int run_tiles(ipr_plan* p, ContractArgs& a, const std::vector<int>& u256, const std::vector<int>& u128,
               const std::vector<int>& m128, char* err, size_t errlen) {
@@ -104,12 +128,12 @@ int run_tiles(ipr_plan* p, ContractArgs& a, const std::vector<int>& u256, const 
     return rc;
 }
 
-// Split [t0, t1) into date tiles.  Tiles start on multiples of 128 (absolute), except that the
-// window is first aligned down to 16; blocks of 128 dates containing any NA take the masked
-// variant (when `use_mask`), aligned unmasked pairs are merged into 256-wide tiles.
+// Split [t0, t1) into date tiles.  Tiles start on granule boundaries (multiples of 128, absolute);
+// granules containing any NA inside the window take the masked variant (when `use_mask`),
+// adjacent unmasked granules are merged into 256-date tiles.
 void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, std::vector<int>& u256, std::vector<int>& u128,
                  std::vector<int>& m128) {
-    const int start = t0 & ~15;
+    const int start = t0 - t0 % kGran;
     std::vector<std::pair<int, bool>> blocks;  // (start, masked)
     for (int b = start; b < t1; b += 128) {
         bool na = false;
@@ -202,7 +226,7 @@ int prepare_obs(ipr_plan* p, char* err, size_t errlen) {
     dim3 block(32, 8);
     dim3 grid((unsigned)((p->n_dates + 31) / 32));
     prep_obs_kernel<<<grid, block, 0, p->stream>>>(p->d_obs, p->n_dates, p->n_dates, p->n_st, p->d_z0, p->d_mask,
-                                                   p->ldz, p->d_flag, p->d_has_na, p->d_counters + 1);
+                                                   p->n_stages, p->d_flag, p->d_has_na, p->d_counters + 1);
     IPR_CUDA(cudaGetLastError());
     p->launches++;
     int bad = 0;
@@ -286,7 +310,9 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     p->n_st = n_st;
     p->s_pad = (int)round_up(n_st, kKT);
     p->n_dates = n_dates;
-    p->ldz = (int)round_up(n_dates, 16) + 256;
+    p->n_gran = (int)((n_dates + kGran - 1) / kGran) + 1;  // +1: a 256-date tile may start on the last granule
+    p->n_stages = p->s_pad / kKT;
+    p->z_doubles = (size_t)p->n_gran * p->n_stages * kBlkDoubles;
     p->pair_capacity = std::max(4 * n_st, 65536);
 #define PLAN_CUDA(call)                   \
     do {                                  \
@@ -302,15 +328,15 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     PLAN_CUDA(cudaMalloc(&p->d_cell, sizeof(double2) * p->c_pad));
     PLAN_CUDA(cudaMalloc(&p->d_st, sizeof(double2) * (p->s_pad + kKT)));
     PLAN_CUDA(cudaMalloc(&p->d_obs, sizeof(double) * (size_t)n_dates * n_st));
-    PLAN_CUDA(cudaMalloc(&p->d_z0, sizeof(double) * (size_t)p->s_pad * p->ldz));
-    PLAN_CUDA(cudaMalloc(&p->d_mask, sizeof(double) * (size_t)p->s_pad * p->ldz));
-    PLAN_CUDA(cudaMalloc(&p->d_flag, p->ldz));
-    PLAN_CUDA(cudaMalloc(&p->d_has_na, p->ldz));
+    PLAN_CUDA(cudaMalloc(&p->d_z0, sizeof(double) * p->z_doubles));
+    PLAN_CUDA(cudaMalloc(&p->d_mask, sizeof(double) * p->z_doubles));
+    PLAN_CUDA(cudaMalloc(&p->d_flag, (size_t)p->n_gran * kGran));
+    PLAN_CUDA(cudaMalloc(&p->d_has_na, (size_t)p->n_gran * kGran));
     PLAN_CUDA(cudaMalloc(&p->d_counters, sizeof(int) * 4));
     PLAN_CUDA(cudaMalloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
-    PLAN_CUDA(cudaMemsetAsync(p->d_z0, 0, sizeof(double) * (size_t)p->s_pad * p->ldz, p->stream));
-    PLAN_CUDA(cudaMemsetAsync(p->d_mask, 0, sizeof(double) * (size_t)p->s_pad * p->ldz, p->stream));
-    PLAN_CUDA(cudaMemsetAsync(p->d_flag, 0, p->ldz, p->stream));
+    PLAN_CUDA(cudaMemsetAsync(p->d_z0, 0, sizeof(double) * p->z_doubles, p->stream));
+    PLAN_CUDA(cudaMemsetAsync(p->d_mask, 0, sizeof(double) * p->z_doubles, p->stream));
+    PLAN_CUDA(cudaMemsetAsync(p->d_flag, 0, (size_t)p->n_gran * kGran, p->stream));
     PLAN_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(int) * 4, p->stream));
     {
         std::vector<double2> h(p->c_pad);
@@ -334,6 +360,13 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
             }
         }
         PLAN_CUDA(cudaMemcpyAsync(p->d_st, hs.data(), sizeof(double2) * hs.size(), cudaMemcpyHostToDevice, p->stream));
+        {
+            const int total = p->n_gran * p->n_stages * kKT;
+            fill_block_coords_kernel<<<(total + 255) / 256, 256, 0, p->stream>>>(p->d_st, p->d_z0, p->d_mask,
+                                                                                 p->n_stages, p->n_gran);
+            PLAN_CUDA(cudaGetLastError());
+            p->launches++;
+        }
         PLAN_CUDA(cudaStreamSynchronize(p->stream));  // staging vectors go out of scope
     }
 #undef PLAN_CUDA
@@ -416,9 +449,9 @@ int ipr_plan_idw(ipr_plan* p, double pw, int32_t t0, int32_t t1, double* d_out, 
     a.ld_out = ld_out;
     a.n_cells = p->n_cells;
     a.s_pad = p->s_pad;
-    a.ldz = p->ldz;
     a.t_lo = t0;
     a.t_hi = t1;
+    a.stagger_cycles = stagger_cycles();
     std::vector<int> u256, u128, m128;
     build_tiles(p, t0, t1, true, u256, u128, m128);
     const double half = pw / 2.0;
@@ -471,14 +504,36 @@ int ipr_plan_cressman(ipr_plan* p, const double* radii_m, int32_t n_radii, int32
         a.ld_out = ld_out;
         a.n_cells = p->n_cells;
         a.s_pad = p->s_pad;
-        a.ldz = p->ldz;
-        a.t_lo = t0;
+            a.t_lo = t0;
         a.t_hi = t1;
+        a.stagger_cycles = stagger_cycles();
         a.wp.a = radii_m[ri] * radii_m[ri];
         rc = run_tiles<kCressman>(p, a, u256, u128, m128, err, errlen);
         if (rc) return rc;
     }
     return IPR_OK;
+}
+
+// tuning experiments only (not declared in the public header): runs the 256-date IDW kernel with
+// parts of its work disabled (see DBG in ipr_kernels.cuh); the output is garbage by construction
+int ipr_debug_variant(ipr_plan* p, int dbg, double* d_out, char* err, size_t errlen) {
+    if (!p || !p->obs_ready || !d_out) return IPR_EINVAL;
+    IPR_CUDA(cudaSetDevice(p->device));
+    ContractArgs a{};
+    a.cell_xy = p->d_cell; a.st_xy = p->d_st; a.z0 = p->d_z0; a.mask = p->d_mask; a.date_flag = p->d_flag;
+    a.out = d_out; a.ld_out = p->n_cells; a.n_cells = p->n_cells; a.s_pad = p->s_pad;
+    a.t_lo = 0; a.t_hi = p->n_dates; a.stagger_cycles = stagger_cycles();
+    std::vector<int> tiles;
+    for (int t = 0; t + 256 <= p->n_dates && (int)tiles.size() < kMaxTilesPerLaunch; t += 256) tiles.push_back(t);
+    switch (dbg) {
+        case 0: return launch_debug<0>(p, a, tiles, err, errlen);
+        case 1: return launch_debug<1>(p, a, tiles, err, errlen);
+        case 2: return launch_debug<2>(p, a, tiles, err, errlen);
+        case 3: return launch_debug<3>(p, a, tiles, err, errlen);
+        case 4: return launch_debug<4>(p, a, tiles, err, errlen);
+        case 7: return launch_debug<7>(p, a, tiles, err, errlen);
+        default: return IPR_EINVAL;
+    }
 }
 
 int ipr_plan_sync(ipr_plan* p) {

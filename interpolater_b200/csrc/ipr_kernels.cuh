@@ -28,6 +28,16 @@ constexpr int kCellsPerCta = kConsumerWarps * 8;     // 64
 constexpr int kKT = 16;                              // stations per pipeline stage
 constexpr int kStages = 4;
 constexpr int kMaxTilesPerLaunch = 56;
+// Device layout of the B operand ("granule blocks"): dates are cut into granules of 128, stations
+// into pipeline stages of kKT; block (g, stage) is ONE contiguous chunk that is already in the
+// padded shared-memory layout, so a stage is refilled by one bulk copy per granule:
+//   [kKT rows][kGranLd doubles]  z0 (or mask) of 128 dates, rows padded by 4 doubles (bank spread)
+//   [kKT double2]                coordinates of the stations of stage+1 (travel one stage ahead)
+constexpr int kGran = 128;
+constexpr int kGranLd = kGran + 4;
+constexpr int kBlkCoordOff = kKT * kGranLd;              // in doubles
+constexpr int kBlkDoubles = kBlkCoordOff + 2 * kKT;      // 2144 doubles = 17152 bytes
+constexpr int kBlkBytes = kBlkDoubles * 8;
 constexpr double kPadCoord = 1e150;                  // padded stations: d^2 ~ 2e300 -> weight ~ 0
 constexpr unsigned long long kNaRealBits = 0x7FF00000000007A2ull;
 
@@ -51,15 +61,15 @@ struct TileList {
 struct ContractArgs {
     const double2* cell_xy;   // [C_pad]
     const double2* st_xy;     // [S_pad + kKT]
-    const double* z0;         // [S_pad][ldz]
-    const double* mask;       // [S_pad][ldz] (masked variants only)
-    const uint8_t* date_flag; // [>= ldz] 0 normal, 1 all-NA layer, 2 exact-zero layer (IDW only)
+    const double* z0;         // granule blocks [n_gran][n_stages][kBlkDoubles]
+    const double* mask;       // same layout (masked variants only)
+    const uint8_t* date_flag; // [n_gran*128] 0 normal, 1 all-NA layer, 2 exact-zero layer (IDW only)
     double* out;              // layer t at out + (t - t_lo) * ld_out
     long long ld_out;
     long long n_cells;
     int s_pad;
-    int ldz;
     int t_lo, t_hi;           // store window [t_lo, t_hi)
+    int stagger_cycles;       // start-up delay of warps 4..7 (de-phases SMSP partner warps)
     WeightParams wp;
     TileList tiles;
 };
@@ -149,42 +159,32 @@ __device__ __forceinline__ double weight_from_d2(double d2, const WeightParams& 
 
 template <int NP, bool MASKED>
 struct SmemLayout {
-    static constexpr int kW = 16 * NP;                // dates per tile
-    static constexpr int kLd = kW + 4;                // padded row (doubles)
-    static constexpr int kRowBytes = kW * 8;
-    static constexpr int kZBytes = kKT * kLd * 8;
-    static constexpr int kCoordOff = kZBytes * (MASKED ? 2 : 1);
-    static constexpr int kStageBytes = kCoordOff + kKT * 16;
+    static_assert(NP == 8 || (NP == 16 && !MASKED), "tile = 1 or 2 granules of z0, or z0 + mask granule");
+    static constexpr int kW = 16 * NP;                          // dates per tile
+    static constexpr int kBlocks = (NP == 16 || MASKED) ? 2 : 1;  // granule blocks per stage
+    static constexpr int kStageBytes = kBlocks * kBlkBytes;
     static constexpr int kBarOff = kStageBytes * kStages;
-    static constexpr int kTotal = kBarOff + 2 * kStages * 8;
-    static constexpr uint32_t kTxBytes = kKT * kRowBytes * (MASKED ? 2 : 1) + kKT * 16;
+    static constexpr int kTotal = kBarOff + kStages * 8 + kStages * 4 + 16;
+    static constexpr uint32_t kTxBytes = kBlocks * kBlkBytes;
 };
 
-
-// Refill one pipeline stage: z0 rows by lanes 0..15, mask rows by lanes 16..31, and the station
-// coordinates of the FOLLOWING stage (they travel one stage ahead of their z rows so that the
-// next stage's weights can be generated underneath this stage's DMMAs).  Called by a whole warp.
+// Refill one pipeline stage: one bulk copy (TMA bulk engine) per granule block.  Called by one lane.
 template <int NP, bool MASKED>
 __device__ __forceinline__ void produce_stage(const ContractArgs& args, unsigned char* smem, uint64_t* full_bar,
-                                              uint64_t* empty_bar, int it, int tile_t0, int lane) {
+                                              int it, int n_stages, int gran0) {
     using L = SmemLayout<NP, MASKED>;
     const int slot = it % kStages;
-    const int j = it / kStages;
     unsigned char* stage = smem + slot * L::kStageBytes;
-    if (lane == 0) {
-        mbar_wait(&empty_bar[slot], (j & 1) ^ 1);
-        mbar_expect_tx(&full_bar[slot], L::kTxBytes);
-    }
-    __syncwarp();
-    const int row = lane & 15;
-    const size_t goff = (size_t)(it * kKT + row) * args.ldz + tile_t0;
-    if (lane < 16) {
-        bulk_g2s(stage + row * L::kLd * 8, args.z0 + goff, L::kRowBytes, &full_bar[slot]);
-    } else if (MASKED) {
-        bulk_g2s(stage + L::kZBytes + row * L::kLd * 8, args.mask + goff, L::kRowBytes, &full_bar[slot]);
-    }
-    if (lane == 0) {
-        bulk_g2s(stage + L::kCoordOff, args.st_xy + (size_t)(it + 1) * kKT, kKT * 16, &full_bar[slot]);
+    // generic-proxy reads of this slot (all warps, ordered by the release counter) precede the
+    // async-proxy writes issued below
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&full_bar[slot], L::kTxBytes);
+    const size_t b0 = ((size_t)gran0 * n_stages + it) * kBlkDoubles;
+    bulk_g2s(stage, args.z0 + b0, kBlkBytes, &full_bar[slot]);
+    if (MASKED) {
+        bulk_g2s(stage + kBlkBytes, args.mask + b0, kBlkBytes, &full_bar[slot]);
+    } else if (NP == 16) {
+        bulk_g2s(stage + kBlkBytes, args.z0 + b0 + (size_t)n_stages * kBlkDoubles, kBlkBytes, &full_bar[slot]);
     }
 }
 
@@ -194,32 +194,38 @@ __device__ __forceinline__ void produce_stage(const ContractArgs& args, unsigned
 //   MASKED : also contract the availability mask (IDW with NA in the tile: 4*S flop/cell-day)
 //   WMODE  : weight function
 // ---------------------------------------------------------------------------------------------
-template <int NP, bool MASKED, int WMODE>
+// DBG (tuning experiments only, results are then WRONG): 1 = B operand not read from shared memory,
+// 2 = stages are not refilled/waited for after the prologue, 4 = weights not generated
+template <int NP, bool MASKED, int WMODE, int DBG = 0>
 __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArgs args) {
     using L = SmemLayout<NP, MASKED>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-    uint64_t* empty_bar = full_bar + kStages;
+    // release counters: a slot is refilled by whichever warp is the LAST to finish reading it, so no
+    // warp ever blocks on "slot empty" (a blocking producer re-synchronises the two warps of an
+    // SM sub-partition every stage and exposes their non-DMMA gaps)
+    int* release_cnt = reinterpret_cast<int*>(full_bar + kStages);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile_t0 = args.tiles.t0[blockIdx.y];
+    const int tile_t0 = args.tiles.t0[blockIdx.y];   // multiple of kGran
+    const int gran0 = tile_t0 / kGran;
     const int n_stages = args.s_pad / kKT;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kConsumerWarps);
+            release_cnt[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
-    // prologue: the first kStages-1 stages
-    if (warp == 0) {
-        for (int it = 0; it < kStages - 1 && it < n_stages; it++)
-            produce_stage<NP, MASKED>(args, smem, full_bar, empty_bar, it, tile_t0, lane);
+    // prologue: fill every slot
+    if (threadIdx.x == 0) {
+        for (int it = 0; it < kStages && it < n_stages; it++)
+            produce_stage<NP, MASKED>(args, smem, full_bar, it, n_stages, gran0);
     }
 
     const int q = lane & 3;   // k index inside a k-step (A column / B row)
@@ -248,24 +254,29 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
         w_cur[kk] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp);
     }
 
+    // de-phase the two warps that share an SM sub-partition (warp w and w+4): the late one runs its
+    // DMMAs while the early one is in its per-stage non-DMMA gap (barrier wait, first LDS, release)
+    if (warp >= kConsumerWarps / 2 && args.stagger_cycles > 0) {
+        const long long t_start = clock64();
+        while (clock64() - t_start < args.stagger_cycles) {
+        }
+    }
+
     for (int it = 0; it < n_stages; it++) {
         const int slot = it % kStages;
         const int j = it / kStages;
         const unsigned char* stage = smem + slot * L::kStageBytes;
         const double* zs = reinterpret_cast<const double*>(stage);
-        const double* ms = reinterpret_cast<const double*>(stage + L::kZBytes);
-        const double2* cs = reinterpret_cast<const double2*>(stage + L::kCoordOff);
-        {
-            // refill the slot freed by iteration it-1 with stage it+kStages-1; warps take turns
-            const int pit = it + kStages - 1;
-            if (pit < n_stages && warp == (it & (kConsumerWarps - 1)))
-                produce_stage<NP, MASKED>(args, smem, full_bar, empty_bar, pit, tile_t0, lane);
-        }
-        mbar_wait(&full_bar[slot], j & 1);
+        const double2* cs = reinterpret_cast<const double2*>(zs + kBlkCoordOff);
+        if (!(DBG & 2) || it < kStages) mbar_wait(&full_bar[slot], j & 1);
 
         double w_next[kKT / 4];
 #pragma unroll
         for (int kk = 0; kk < kKT / 4; kk++) {
+            if (DBG & 4) {
+                w_next[kk] = w_cur[kk] + 1e-9;
+                continue;
+            }
             const double2 s = cs[kk * 4 + q];
             const double dx = cxy.x - s.x, dy = cxy.y - s.y;
             w_next[kk] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp);
@@ -274,11 +285,14 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
         for (int kk = 0; kk < kKT / 4; kk++) {
             const double a = w_cur[kk];
             wsum += a;
-            const double* zrow = zs + (kk * 4 + q) * L::kLd + 2 * r;
-            const double* mrow = ms + (kk * 4 + q) * L::kLd + 2 * r;
+            const double* zrow = zs + (kk * 4 + q) * kGranLd + 2 * r;
+            const double* mrow = zrow + kBlkDoubles;  // mask granule block follows the z0 block
 #pragma unroll
             for (int i = 0; i < NP; i++) {
-                const double2 b = *reinterpret_cast<const double2*>(zrow + 16 * i);
+                double2 b;
+                // column group i lives in granule block i/8 (256-date tiles span two blocks)
+                if (DBG & 1) b = make_double2(a, a);
+                else b = *reinterpret_cast<const double2*>(zrow + (i >> 3) * kBlkDoubles + 16 * (i & 7));
                 dmma884(acc[2 * i][0], acc[2 * i][1], a, b.x);
                 dmma884(acc[2 * i + 1][0], acc[2 * i + 1][1], a, b.y);
                 if (MASKED) {
@@ -288,8 +302,17 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
                 }
             }
         }
+        // release the slot; the last warp to do so refills it with stage it + kStages
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[slot]);
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&release_cnt[slot], 1) == kConsumerWarps - 1) {
+                release_cnt[slot] = 0;
+                __threadfence_block();
+                if (!(DBG & 2) && it + kStages < n_stages)
+                    produce_stage<NP, MASKED>(args, smem, full_bar, it + kStages, n_stages, gran0);
+            }
+        }
 #pragma unroll
         for (int kk = 0; kk < kKT / 4; kk++) w_cur[kk] = w_next[kk];
     }
@@ -300,6 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
     wsum += __shfl_xor_sync(0xffffffffu, wsum, 2);
     const double na = __longlong_as_double((long long)kNaRealBits);
     if (cell >= args.n_cells) return;
+    const double inv_wsum = 1.0 / wsum;
 #pragma unroll
     for (int i = 0; i < NP; i++) {
         // thread holds dates tile_t0 + 16 i + 4 q + {0,1,2,3} for its cell:
@@ -312,7 +336,8 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
             const int c = e >> 1;
             const double numer = acc[f][c];
             const double denom = MASKED ? accm[f][c] : wsum;
-            double v = numer / denom;
+            // date-independent denominator: one true division per thread (inv_wsum), then multiplies
+            double v = MASKED ? numer / denom : numer * inv_wsum;
             // R/IDW.R:332,339 ; R/Cressman.R:317 : !is.finite(v) | denom == 0 -> NA
             if (!isfinite(v) || denom == 0.0) v = na;
             if (WMODE != kCressman) {
@@ -330,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
 //   block = (32 dates, 8 station stripes)
 // ---------------------------------------------------------------------------------------------
 __global__ void prep_obs_kernel(const double* __restrict__ obs, long long ld_obs, int n_dates, int n_st,
-                                double* __restrict__ z0, double* __restrict__ mask, int ldz,
+                                double* __restrict__ z0, double* __restrict__ mask, int n_stages,
                                 uint8_t* __restrict__ date_flag, uint8_t* __restrict__ date_has_na,
                                 int* __restrict__ nonfinite_count) {
     __shared__ int s_cnt[8][32];
@@ -338,11 +363,13 @@ __global__ void prep_obs_kernel(const double* __restrict__ obs, long long ld_obs
     const int t = blockIdx.x * 32 + threadIdx.x;
     int cnt = 0, big = 0, bad = 0;
     if (t < n_dates) {
+        const size_t gbase = (size_t)(t / kGran) * n_stages * kBlkDoubles + (t % kGran);
         for (int s = threadIdx.y; s < n_st; s += 8) {
             const double v = obs[(long long)s * ld_obs + t];
             const bool isna = (v != v);
-            z0[(long long)s * ldz + t] = isna ? 0.0 : v;
-            mask[(long long)s * ldz + t] = isna ? 0.0 : 1.0;
+            const size_t off = gbase + (size_t)(s / kKT) * kBlkDoubles + (s % kKT) * kGranLd;
+            z0[off] = isna ? 0.0 : v;
+            mask[off] = isna ? 0.0 : 1.0;
             if (!isna) {
                 cnt++;
                 if (!(fabs(v) < 1e-12)) big = 1;
@@ -363,6 +390,22 @@ __global__ void prep_obs_kernel(const double* __restrict__ obs, long long ld_obs
         date_flag[t] = (c == 0) ? 1 : (b ? 0 : 2);
         date_has_na[t] = (c < n_st) ? 1 : 0;
     }
+}
+
+// writes the station coordinates of stage+1 into the tail of every granule block (once per plan)
+__global__ void fill_block_coords_kernel(const double2* __restrict__ st_xy, double* __restrict__ z0,
+                                         double* __restrict__ mask, int n_stages, int n_gran) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = n_gran * n_stages * kKT;
+    if (idx >= total) return;
+    const int k = idx % kKT;
+    const int blk = idx / kKT;            // g * n_stages + stage
+    const int stage = blk % n_stages;
+    const double2 c = st_xy[(stage + 1) * kKT + k];
+    double2* dz = reinterpret_cast<double2*>(z0 + (size_t)blk * kBlkDoubles + kBlkCoordOff);
+    double2* dm = reinterpret_cast<double2*>(mask + (size_t)blk * kBlkDoubles + kBlkCoordOff);
+    dz[k] = c;
+    dm[k] = c;
 }
 
 // ---------------------------------------------------------------------------------------------
