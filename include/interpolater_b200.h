@@ -97,6 +97,11 @@ int ipr_plan_cressman(ipr_plan* plan, const double* radii_m, int32_t n_radii,
                       int32_t t0, int32_t t1, double* d_out, int64_t ld_out,
                       int64_t stack_stride, char* err, size_t errlen);
 
+/* Drops the cached A operand (the cell x station weights, kept in HBM between calls because the
+ * geometry of a plan never changes), so that the next call regenerates it.  The benchmark calls
+ * this every step so that a timed step contains the whole hot path. */
+void ipr_plan_reset_cache(ipr_plan* plan);
+
 int ipr_plan_sync(ipr_plan* plan);
 /* CUDA events on the plan's stream, for timing exactly what the plan launched */
 int ipr_plan_timer_start(ipr_plan* plan);

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libinterpolater_b200.so")
+LIB_PATH = os.environ.get("IPR_LIB_OVERRIDE") or os.path.join(_HERE, "lib", "libinterpolater_b200.so")
 
 IPR_OK = 0
 ERRLEN = 512
@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "ipr_version", "ipr_device_count", "ipr_na_real",
     "ipr_idw_f64", "ipr_cressman_f64",
     "ipr_plan_create", "ipr_plan_destroy", "ipr_plan_set_obs", "ipr_plan_set_obs_device",
-    "ipr_plan_idw", "ipr_plan_cressman", "ipr_plan_sync",
+    "ipr_plan_idw", "ipr_plan_cressman", "ipr_plan_sync", "ipr_plan_reset_cache",
     "ipr_plan_timer_start", "ipr_plan_timer_stop", "ipr_plan_launch_count", "ipr_plan_zero_pairs",
     "ipr_plan_stream", "ipr_host_alloc", "ipr_host_free",
 ]
@@ -75,6 +75,8 @@ def load() -> C.CDLL:
     lib.ipr_plan_cressman.restype = C.c_int
     lib.ipr_plan_cressman.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int64, C.c_int64,
                                       C.c_char_p, C.c_size_t]
+    lib.ipr_plan_reset_cache.restype = None
+    lib.ipr_plan_reset_cache.argtypes = [vp]
     lib.ipr_plan_sync.restype = C.c_int
     lib.ipr_plan_sync.argtypes = [vp]
     lib.ipr_plan_timer_start.restype = C.c_int

@@ -38,15 +38,6 @@ void set_err(char* err, size_t errlen, const char* fmt, ...) {
     } while (0)
 
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
-// start-up de-phasing of the two warps per SM sub-partition (cycles); tunable for experiments
-inline int stagger_cycles() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("IPR_STAGGER_CYCLES");
-        v = e ? atoi(e) : 1800;
-    }
-    return v;
-}
 inline double canon_zero(double v) { return v == 0.0 ? 0.0 : v; }  // -0 -> +0
 
 }  // namespace
@@ -77,15 +68,25 @@ struct ipr_plan {
     std::vector<uint8_t> h_has_na;
     bool obs_ready = false;
     long long launches = 0;
+    // A-operand cache (weights in DMMA fragment order) for a chunk of cell tiles + per-cell sums
+    double* d_wfrag = nullptr;
+    double* d_wsum = nullptr;
+    int w_chunk_tiles = 0;   // capacity of d_wfrag in cell tiles
+    int w_mode = -1;         // what the cache currently holds: weight mode, parameter, first tile
+    double w_param = 0.0;
+    int w_tile0 = -1;
 };
 
 namespace {
 
-template <int NP, bool MASKED, int WMODE>
+void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, std::vector<int>& u256, std::vector<int>& u128,
+                 std::vector<int>& m128);
+
+template <int NP, bool MASKED>
 int launch_contract(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles, char* err, size_t errlen) {
     using L = SmemLayout<NP, MASKED>;
     static bool configured[64] = {false};
-    auto kern = contract_kernel<NP, MASKED, WMODE>;
+    auto kern = contract_kernel<NP, MASKED>;
     if (!configured[p->device & 63]) {
         IPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         configured[p->device & 63] = true;
@@ -94,38 +95,92 @@ int launch_contract(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles,
         const int n = (int)std::min<size_t>(kMaxTilesPerLaunch, tiles.size() - i0);
         a.tiles.n = n;
         for (int i = 0; i < n; i++) a.tiles.t0[i] = tiles[i0 + i];
-        dim3 grid((unsigned)(p->c_pad / kCellsPerCta), (unsigned)n);
-        kern<<<grid, kThreads, L::kTotal, p->stream>>>(a);
+        const long long blocks = (long long)a.n_cell_tiles * n;
+        kern<<<(unsigned)blocks, kThreads, L::kTotal, p->stream>>>(a);
         IPR_CUDA(cudaGetLastError());
         p->launches++;
     }
     return IPR_OK;
 }
 
-template <int DBG>
-int launch_debug(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles, char* err, size_t errlen) {
-    using L = SmemLayout<16, false>;
-    auto kern = contract_kernel<16, false, kIdwP2, DBG>;
-    IPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    a.tiles.n = (int)tiles.size();
-    for (size_t i = 0; i < tiles.size(); i++) a.tiles.t0[i] = tiles[i];
-    dim3 grid((unsigned)(p->c_pad / kCellsPerCta), (unsigned)tiles.size());
-    kern<<<grid, kThreads, L::kTotal, p->stream>>>(a);
+// Makes sure the A-operand cache holds the weights of `mode`/`wp` for the cell tiles starting at
+// tile0 (regenerated only when something changed: the geometry is fixed for the plan's lifetime).
+int ensure_weights(ipr_plan* p, int mode, const WeightParams& wp, int tile0, int n_tiles, char* err, size_t errlen) {
+    const double key = (mode == kIdwEvenP) ? (double)wp.n : wp.a;
+    if (p->w_mode == mode && p->w_param == key && p->w_tile0 == tile0) return IPR_OK;
+    WeightArgs w{};
+    w.cell_xy = p->d_cell;
+    w.st_xy = p->d_st;
+    w.wfrag = p->d_wfrag;
+    w.wsum = p->d_wsum;
+    w.cell_tile0 = tile0;
+    w.n_cell_tiles = n_tiles;
+    w.n_stages = p->n_stages;
+    w.wp = wp;
+    switch (mode) {
+        case kIdwP2: weights_kernel<kIdwP2><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
+        case kIdwEvenP: weights_kernel<kIdwEvenP><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
+        case kIdwGenericP: weights_kernel<kIdwGenericP><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
+        default: weights_kernel<kCressman><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
+    }
     IPR_CUDA(cudaGetLastError());
+    p->launches++;
+    p->w_mode = mode;
+    p->w_param = key;
+    p->w_tile0 = tile0;
     return IPR_OK;
 }
 
-template <int WMODE>
-int run_tiles(ipr_plan* p, ContractArgs& a, const std::vector<int>& u256, const std::vector<int>& u128,
-              const std::vector<int>& m128, char* err, size_t errlen) {
-    int rc = IPR_OK;
-    if (!u256.empty() && (rc = launch_contract<16, false, WMODE>(p, a, u256, err, errlen))) return rc;
-    if (!u128.empty() && (rc = launch_contract<8, false, WMODE>(p, a, u128, err, errlen))) return rc;
-    if (WMODE != kCressman) {
-        if (!m128.empty() && (rc = launch_contract<8, true, (WMODE == kCressman ? kIdwP2 : WMODE)>(p, a, m128, err, errlen)))
-            return rc;
+// Lazily sizes the A-operand cache: the whole grid if it fits in half of the free device memory
+// (IPR_WCACHE_MB overrides), otherwise the largest chunk of cell tiles that does.
+int ensure_wcache(ipr_plan* p, char* err, size_t errlen) {
+    if (p->d_wfrag) return IPR_OK;
+    const long long total_tiles = p->c_pad / kCellsPerCta;
+    const size_t tile_bytes = (size_t)p->n_stages * kWStageDoubles * sizeof(double);
+    size_t free_b = 0, total_b = 0;
+    IPR_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = free_b / 2;
+    if (const char* e = getenv("IPR_WCACHE_MB")) budget = (size_t)atoll(e) << 20;
+    long long tiles = std::min<long long>(total_tiles, (long long)(budget / tile_bytes));
+    if (tiles < 1) {
+        set_err(err, errlen, "not enough device memory for the weight cache (%zu bytes per cell tile)", tile_bytes);
+        return IPR_ENOMEM;
     }
-    return rc;
+    IPR_CUDA(cudaMalloc(&p->d_wfrag, tile_bytes * tiles));
+    p->w_chunk_tiles = (int)tiles;
+    return IPR_OK;
+}
+
+// One weight function over the date range: loops over cell-tile chunks of the A-operand cache
+int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int t0, int t1, double* d_out,
+                    long long ld_out, char* err, size_t errlen) {
+    int rc = ensure_wcache(p, err, errlen);
+    if (rc) return rc;
+    std::vector<int> u256, u128, m128;
+    build_tiles(p, t0, t1, idw, u256, u128, m128);
+    const int total_tiles = (int)(p->c_pad / kCellsPerCta);
+    for (int tile0 = 0; tile0 < total_tiles; tile0 += p->w_chunk_tiles) {
+        const int n_tiles = std::min(p->w_chunk_tiles, total_tiles - tile0);
+        if ((rc = ensure_weights(p, mode, wp, tile0, n_tiles, err, errlen))) return rc;
+        ContractArgs a{};
+        a.wfrag = p->d_wfrag;
+        a.wsum = p->d_wsum;
+        a.z0 = p->d_z0;
+        a.mask = p->d_mask;
+        a.date_flag = idw ? p->d_flag : nullptr;
+        a.out = d_out;
+        a.ld_out = ld_out;
+        a.n_cells = p->n_cells;
+        a.cell_tile0 = tile0;
+        a.n_cell_tiles = n_tiles;
+        a.n_stages = p->n_stages;
+        a.t_lo = t0;
+        a.t_hi = t1;
+        if (!u256.empty() && (rc = launch_contract<16, false>(p, a, u256, err, errlen))) return rc;
+        if (!u128.empty() && (rc = launch_contract<8, false>(p, a, u128, err, errlen))) return rc;
+        if (!m128.empty() && (rc = launch_contract<8, true>(p, a, m128, err, errlen))) return rc;
+    }
+    return IPR_OK;
 }
 
 // Split [t0, t1) into date tiles.  Tiles start on granule boundaries (multiples of 128, absolute);
@@ -334,6 +389,7 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     PLAN_CUDA(cudaMalloc(&p->d_has_na, (size_t)p->n_gran * kGran));
     PLAN_CUDA(cudaMalloc(&p->d_counters, sizeof(int) * 4));
     PLAN_CUDA(cudaMalloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
+    PLAN_CUDA(cudaMalloc(&p->d_wsum, sizeof(double) * p->c_pad));
     PLAN_CUDA(cudaMemsetAsync(p->d_z0, 0, sizeof(double) * p->z_doubles, p->stream));
     PLAN_CUDA(cudaMemsetAsync(p->d_mask, 0, sizeof(double) * p->z_doubles, p->stream));
     PLAN_CUDA(cudaMemsetAsync(p->d_flag, 0, (size_t)p->n_gran * kGran, p->stream));
@@ -360,13 +416,6 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
             }
         }
         PLAN_CUDA(cudaMemcpyAsync(p->d_st, hs.data(), sizeof(double2) * hs.size(), cudaMemcpyHostToDevice, p->stream));
-        {
-            const int total = p->n_gran * p->n_stages * kKT;
-            fill_block_coords_kernel<<<(total + 255) / 256, 256, 0, p->stream>>>(p->d_st, p->d_z0, p->d_mask,
-                                                                                 p->n_stages, p->n_gran);
-            PLAN_CUDA(cudaGetLastError());
-            p->launches++;
-        }
         PLAN_CUDA(cudaStreamSynchronize(p->stream));  // staging vectors go out of scope
     }
 #undef PLAN_CUDA
@@ -395,6 +444,8 @@ void ipr_plan_destroy(ipr_plan* p) {
     cudaFree(p->d_fix_cell);
     cudaFree(p->d_fix_off);
     cudaFree(p->d_fix_st);
+    cudaFree(p->d_wfrag);
+    cudaFree(p->d_wsum);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -439,32 +490,19 @@ int ipr_plan_idw(ipr_plan* p, double pw, int32_t t0, int32_t t1, double* d_out, 
     }
     if (t0 == t1) return IPR_OK;
     IPR_CUDA(cudaSetDevice(p->device));
-    ContractArgs a{};
-    a.cell_xy = p->d_cell;
-    a.st_xy = p->d_st;
-    a.z0 = p->d_z0;
-    a.mask = p->d_mask;
-    a.date_flag = p->d_flag;
-    a.out = d_out;
-    a.ld_out = ld_out;
-    a.n_cells = p->n_cells;
-    a.s_pad = p->s_pad;
-    a.t_lo = t0;
-    a.t_hi = t1;
-    a.stagger_cycles = stagger_cycles();
-    std::vector<int> u256, u128, m128;
-    build_tiles(p, t0, t1, true, u256, u128, m128);
+    WeightParams wp{};
+    int mode;
     const double half = pw / 2.0;
     if (pw == 2.0) {
-        rc = run_tiles<kIdwP2>(p, a, u256, u128, m128, err, errlen);
+        mode = kIdwP2;
     } else if (half == std::floor(half) && half <= 16.0) {
-        a.wp.n = (int)half;
-        rc = run_tiles<kIdwEvenP>(p, a, u256, u128, m128, err, errlen);
+        mode = kIdwEvenP;
+        wp.n = (int)half;
     } else {
-        a.wp.a = -half;
-        rc = run_tiles<kIdwGenericP>(p, a, u256, u128, m128, err, errlen);
+        mode = kIdwGenericP;
+        wp.a = -half;
     }
-    if (rc) return rc;
+    if ((rc = run_contraction(p, mode, wp, true, t0, t1, d_out, ld_out, err, errlen))) return rc;
     if (p->n_fix > 0) {
         dim3 grid((unsigned)((t1 - t0 + 127) / 128), (unsigned)p->n_fix);
         idw_zero_fix_kernel<<<grid, 128, 0, p->stream>>>(p->d_fix_cell, p->d_fix_off, p->d_fix_st, p->n_fix, p->d_obs,
@@ -491,49 +529,18 @@ int ipr_plan_cressman(ipr_plan* p, const double* radii_m, int32_t n_radii, int32
     }
     if (t0 == t1) return IPR_OK;
     IPR_CUDA(cudaSetDevice(p->device));
-    std::vector<int> u256, u128, m128;
-    build_tiles(p, t0, t1, false, u256, u128, m128);
     for (int ri = 0; ri < n_radii; ri++) {
-        ContractArgs a{};
-        a.cell_xy = p->d_cell;
-        a.st_xy = p->d_st;
-        a.z0 = p->d_z0;
-        a.mask = p->d_mask;
-        a.date_flag = p->d_flag;
-        a.out = d_out + (size_t)ri * stack_stride;
-        a.ld_out = ld_out;
-        a.n_cells = p->n_cells;
-        a.s_pad = p->s_pad;
-            a.t_lo = t0;
-        a.t_hi = t1;
-        a.stagger_cycles = stagger_cycles();
-        a.wp.a = radii_m[ri] * radii_m[ri];
-        rc = run_tiles<kCressman>(p, a, u256, u128, m128, err, errlen);
-        if (rc) return rc;
+        WeightParams wp{};
+        wp.a = radii_m[ri] * radii_m[ri];
+        if ((rc = run_contraction(p, kCressman, wp, false, t0, t1, d_out + (size_t)ri * stack_stride, ld_out, err,
+                                  errlen)))
+            return rc;
     }
     return IPR_OK;
 }
 
-// tuning experiments only (not declared in the public header): runs the 256-date IDW kernel with
-// parts of its work disabled (see DBG in ipr_kernels.cuh); the output is garbage by construction
-int ipr_debug_variant(ipr_plan* p, int dbg, double* d_out, char* err, size_t errlen) {
-    if (!p || !p->obs_ready || !d_out) return IPR_EINVAL;
-    IPR_CUDA(cudaSetDevice(p->device));
-    ContractArgs a{};
-    a.cell_xy = p->d_cell; a.st_xy = p->d_st; a.z0 = p->d_z0; a.mask = p->d_mask; a.date_flag = p->d_flag;
-    a.out = d_out; a.ld_out = p->n_cells; a.n_cells = p->n_cells; a.s_pad = p->s_pad;
-    a.t_lo = 0; a.t_hi = p->n_dates; a.stagger_cycles = stagger_cycles();
-    std::vector<int> tiles;
-    for (int t = 0; t + 256 <= p->n_dates && (int)tiles.size() < kMaxTilesPerLaunch; t += 256) tiles.push_back(t);
-    switch (dbg) {
-        case 0: return launch_debug<0>(p, a, tiles, err, errlen);
-        case 1: return launch_debug<1>(p, a, tiles, err, errlen);
-        case 2: return launch_debug<2>(p, a, tiles, err, errlen);
-        case 3: return launch_debug<3>(p, a, tiles, err, errlen);
-        case 4: return launch_debug<4>(p, a, tiles, err, errlen);
-        case 7: return launch_debug<7>(p, a, tiles, err, errlen);
-        default: return IPR_EINVAL;
-    }
+void ipr_plan_reset_cache(ipr_plan* p) {
+    if (p) p->w_mode = -1;
 }
 
 int ipr_plan_sync(ipr_plan* p) {

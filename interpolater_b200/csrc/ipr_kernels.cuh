@@ -3,18 +3,25 @@
 // Math (reference: R/IDW.R:260-342, R/Cressman.R:279-321 — restated in oracle/reference_port.py):
 //   IDW       out[c,t] = sum_s w(c,s) z0[s,t] / sum_s w(c,s) m[s,t],  w = d(c,s)^-p
 //   Cressman  out[c,t] = sum_s w(c,s) z0[s,t] / sum_s w(c,s),         w = (R^2-d^2)/(R^2+d^2), 0 if d > R
-// i.e. a dense FP64 GEMM  [cells x stations] * [stations x dates]  whose A operand (the weights)
-// is never materialised: every thread generates its A fragment element in registers from the cell
-// and station coordinates, directly in the DMMA.8x8x4 register layout
-// (a[row = lane/4][k = lane%4]), and feeds it to 2*NP accumulators fragments covering 16*NP dates.
+// i.e. a dense FP64 GEMM  [cells x stations] * [stations x dates]  on the FP64 tensor pipe
+// (mma.sync m8n8k4 -> SASS DMMA.8x8x4, the only FP64 tensor op sm_100 has; tcgen05 has no f64 kind).
 //
-// B operand (z0 / mask rows, station-major, dates contiguous) is streamed L2 -> shared memory
-// with cp.async.bulk (TMA bulk engine, UBLKCP) through a kStages-deep mbarrier full/empty
-// pipeline; the refill of a stage is issued by one warp per iteration, in rotation.  Shared rows are padded by 4 doubles so that the
-// LDS.128 B-fragment reads (4 stations x 2 adjacent dates per quarter-warp) are conflict-free.
-//
-// CTA = 8 warps (8 cells each); tile = 64 cells x 16*NP dates;
-// accumulators 8*NP doubles/thread (NP=16 -> 128 registers).  One CTA per SM.
+// Two kernels:
+//   weights_kernel   generates the A operand ONCE per (geometry, weight function): every thread
+//                    computes its weights directly in the DMMA A-fragment register layout
+//                    (a[row = lane/4][k = lane%4]) and streams them to HBM in fragment order, plus
+//                    the per-cell weight sum.  (Generating weights inside the contraction costs
+//                    ~10 FP64-pipe instructions per weight per 256 dates — the FP64 pipe is the
+//                    roofline here, HBM is idle — so the weights are traded to HBM: +0.3 % time for
+//                    the generation pass, -7 % in the contraction.)
+//   contract_kernel  C tile = 64 cells x (128|256) dates per CTA, 8 warps x (8 cells x all dates),
+//                    accumulators in registers (128/thread).  A fragments: one coalesced LDG.64 per
+//                    lane per k-step, prefetched a stage ahead.  B (z0 / mask granule blocks, see
+//                    below): L2 -> shared memory with cp.async.bulk (TMA bulk engine, UBLKCP) through
+//                    a kStages-deep mbarrier pipeline; a slot is refilled by the last warp that
+//                    releases it, so no warp ever blocks on "slot empty".  Shared rows are padded
+//                    by 4 doubles: the LDS.128 B-fragment reads are bank-conflict free.
+//                    Epilogue: normalise, NA rule, per-date early-outs, store (cells contiguous).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -25,19 +32,26 @@ namespace ipr {
 constexpr int kConsumerWarps = 8;
 constexpr int kThreads = kConsumerWarps * 32;
 constexpr int kCellsPerCta = kConsumerWarps * 8;     // 64
-constexpr int kKT = 16;                              // stations per pipeline stage
-constexpr int kStages = 4;
+#ifndef IPR_KT
+#define IPR_KT 32
+#endif
+#ifndef IPR_STAGES
+#define IPR_STAGES 3
+#endif
+constexpr int kKT = IPR_KT;                          // stations per pipeline stage
+constexpr int kKSteps = kKT / 4;                     // DMMA k-steps per stage
+constexpr int kStages = IPR_STAGES;
 constexpr int kMaxTilesPerLaunch = 56;
 // Device layout of the B operand ("granule blocks"): dates are cut into granules of 128, stations
-// into pipeline stages of kKT; block (g, stage) is ONE contiguous chunk that is already in the
-// padded shared-memory layout, so a stage is refilled by one bulk copy per granule:
-//   [kKT rows][kGranLd doubles]  z0 (or mask) of 128 dates, rows padded by 4 doubles (bank spread)
-//   [kKT double2]                coordinates of the stations of stage+1 (travel one stage ahead)
+// into pipeline stages of kKT; block (g, stage) = [kKT rows][kGranLd doubles] is ONE contiguous
+// chunk that is already in the padded shared-memory layout, so a stage is refilled by one bulk
+// copy per granule (33 row-sized copies per stage were measured to cap the kernel at 70 % of peak).
 constexpr int kGran = 128;
 constexpr int kGranLd = kGran + 4;
-constexpr int kBlkCoordOff = kKT * kGranLd;              // in doubles
-constexpr int kBlkDoubles = kBlkCoordOff + 2 * kKT;      // 2144 doubles = 17152 bytes
+constexpr int kBlkDoubles = kKT * kGranLd;
 constexpr int kBlkBytes = kBlkDoubles * 8;
+// A operand cache: weights in fragment order, [cell tile][stage][k-step][warp][lane]
+constexpr int kWStageDoubles = kKSteps * kThreads;
 constexpr double kPadCoord = 1e150;                  // padded stations: d^2 ~ 2e300 -> weight ~ 0
 constexpr unsigned long long kNaRealBits = 0x7FF00000000007A2ull;
 
@@ -59,19 +73,28 @@ struct TileList {
 };
 
 struct ContractArgs {
-    const double2* cell_xy;   // [C_pad]
-    const double2* st_xy;     // [S_pad + kKT]
+    const double* wfrag;      // A operand cache for cell tiles [cell_tile0, cell_tile0 + n_cell_tiles)
+    const double* wsum;       // [c_pad] per-cell sum of weights over all stations
     const double* z0;         // granule blocks [n_gran][n_stages][kBlkDoubles]
     const double* mask;       // same layout (masked variants only)
-    const uint8_t* date_flag; // [n_gran*128] 0 normal, 1 all-NA layer, 2 exact-zero layer (IDW only)
+    const uint8_t* date_flag; // IDW: 0 normal, 1 all-NA layer, 2 exact-zero layer; nullptr for Cressman
     double* out;              // layer t at out + (t - t_lo) * ld_out
     long long ld_out;
     long long n_cells;
-    int s_pad;
+    int cell_tile0, n_cell_tiles;
+    int n_stages;
     int t_lo, t_hi;           // store window [t_lo, t_hi)
-    int stagger_cycles;       // start-up delay of warps 4..7 (de-phases SMSP partner warps)
-    WeightParams wp;
     TileList tiles;
+};
+
+struct WeightArgs {
+    const double2* cell_xy;   // [c_pad]
+    const double2* st_xy;     // [s_pad]
+    double* wfrag;            // chunk base
+    double* wsum;             // [c_pad]
+    int cell_tile0, n_cell_tiles;
+    int n_stages;
+    WeightParams wp;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -160,7 +183,7 @@ __device__ __forceinline__ double weight_from_d2(double d2, const WeightParams& 
 template <int NP, bool MASKED>
 struct SmemLayout {
     static_assert(NP == 8 || (NP == 16 && !MASKED), "tile = 1 or 2 granules of z0, or z0 + mask granule");
-    static constexpr int kW = 16 * NP;                          // dates per tile
+    static constexpr int kW = 16 * NP;                            // dates per tile
     static constexpr int kBlocks = (NP == 16 || MASKED) ? 2 : 1;  // granule blocks per stage
     static constexpr int kStageBytes = kBlocks * kBlkBytes;
     static constexpr int kBarOff = kStageBytes * kStages;
@@ -171,7 +194,7 @@ struct SmemLayout {
 // Refill one pipeline stage: one bulk copy (TMA bulk engine) per granule block.  Called by one lane.
 template <int NP, bool MASKED>
 __device__ __forceinline__ void produce_stage(const ContractArgs& args, unsigned char* smem, uint64_t* full_bar,
-                                              int it, int n_stages, int gran0) {
+                                              int it, int gran0) {
     using L = SmemLayout<NP, MASKED>;
     const int slot = it % kStages;
     unsigned char* stage = smem + slot * L::kStageBytes;
@@ -179,38 +202,84 @@ __device__ __forceinline__ void produce_stage(const ContractArgs& args, unsigned
     // async-proxy writes issued below
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&full_bar[slot], L::kTxBytes);
-    const size_t b0 = ((size_t)gran0 * n_stages + it) * kBlkDoubles;
+    const size_t b0 = ((size_t)gran0 * args.n_stages + it) * kBlkDoubles;
     bulk_g2s(stage, args.z0 + b0, kBlkBytes, &full_bar[slot]);
     if (MASKED) {
         bulk_g2s(stage + kBlkBytes, args.mask + b0, kBlkBytes, &full_bar[slot]);
     } else if (NP == 16) {
-        bulk_g2s(stage + kBlkBytes, args.z0 + b0 + (size_t)n_stages * kBlkDoubles, kBlkBytes, &full_bar[slot]);
+        bulk_g2s(stage + kBlkBytes, args.z0 + b0 + (size_t)args.n_stages * kBlkDoubles, kBlkBytes, &full_bar[slot]);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused weight-generation + DMMA contraction + normalise epilogue
+// A operand: weights in DMMA fragment order + per-cell weight sums.  One CTA per cell tile.
+// ---------------------------------------------------------------------------------------------
+template <int WMODE>
+__global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args) {
+    constexpr int kChunk = 1024;  // stations staged in shared memory at a time (16 KB)
+    __shared__ double2 s_st[kChunk];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q = lane & 3;   // station inside the k-step (A column)
+    const int r = lane >> 2;  // cell row of the fragment
+    const int ct = args.cell_tile0 + blockIdx.x;
+    const long long cell = (long long)ct * kCellsPerCta + warp * 8 + r;
+    const double2 cxy = args.cell_xy[cell];
+    double* dst = args.wfrag + (size_t)blockIdx.x * args.n_stages * kWStageDoubles + threadIdx.x;
+    double wsum0 = 0.0, wsum1 = 0.0, wsum2 = 0.0, wsum3 = 0.0;
+    const int s_pad = args.n_stages * kKT;
+    for (int s0 = 0; s0 < s_pad; s0 += kChunk) {
+        const int n = min(kChunk, s_pad - s0);  // multiple of kKT
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kThreads) s_st[i] = args.st_xy[s0 + i];
+        __syncthreads();
+        double* d = dst + (size_t)(s0 / 4) * kThreads;
+        // 4 independent k-steps per iteration: the reciprocal chains overlap
+        for (int ks = 0; ks < n / 4; ks += 4) {
+            double w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const double2 s = s_st[(ks + u) * 4 + q];
+                const double dx = cxy.x - s.x, dy = cxy.y - s.y;
+                w[u] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp);
+            }
+            wsum0 += w[0];
+            wsum1 += w[1];
+            wsum2 += w[2];
+            wsum3 += w[3];
+#pragma unroll
+            for (int u = 0; u < 4; u++) __stcs(d + (size_t)(ks + u) * kThreads, w[u]);
+        }
+    }
+    // fixed summation order: ((k-steps 0,4,8..) + (1,5,..)) + ((2,6,..) + (3,7,..)), then the quad
+    double wsum = (wsum0 + wsum1) + (wsum2 + wsum3);
+    wsum += __shfl_xor_sync(0xffffffffu, wsum, 1);
+    wsum += __shfl_xor_sync(0xffffffffu, wsum, 2);
+    if (q == 0) args.wsum[cell] = wsum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DMMA contraction + normalise epilogue
 //   NP     : number of 16-date column groups per tile (tile width 16*NP dates)
 //   MASKED : also contract the availability mask (IDW with NA in the tile: 4*S flop/cell-day)
-//   WMODE  : weight function
+// grid.x = n_cell_tiles * n_tiles, date tile fastest: CTAs that run together share the A tile
+// through L2 and the whole B operand (tens of MB) stays L2-resident.
 // ---------------------------------------------------------------------------------------------
-// DBG (tuning experiments only, results are then WRONG): 1 = B operand not read from shared memory,
-// 2 = stages are not refilled/waited for after the prologue, 4 = weights not generated
-template <int NP, bool MASKED, int WMODE, int DBG = 0>
+template <int NP, bool MASKED>
 __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArgs args) {
     using L = SmemLayout<NP, MASKED>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-    // release counters: a slot is refilled by whichever warp is the LAST to finish reading it, so no
-    // warp ever blocks on "slot empty" (a blocking producer re-synchronises the two warps of an
-    // SM sub-partition every stage and exposes their non-DMMA gaps)
+    // release counters: a slot is refilled by whichever warp is the LAST to finish reading it
     int* release_cnt = reinterpret_cast<int*>(full_bar + kStages);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile_t0 = args.tiles.t0[blockIdx.y];   // multiple of kGran
+    const int tile_idx = blockIdx.x % args.tiles.n;
+    const int ct_local = blockIdx.x / args.tiles.n;
+    const int tile_t0 = args.tiles.t0[tile_idx];   // multiple of kGran
     const int gran0 = tile_t0 / kGran;
-    const int n_stages = args.s_pad / kKT;
+    const int n_stages = args.n_stages;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
@@ -221,17 +290,14 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-
-    // prologue: fill every slot
     if (threadIdx.x == 0) {
-        for (int it = 0; it < kStages && it < n_stages; it++)
-            produce_stage<NP, MASKED>(args, smem, full_bar, it, n_stages, gran0);
+        for (int it = 0; it < kStages && it < n_stages; it++) produce_stage<NP, MASKED>(args, smem, full_bar, it, gran0);
     }
 
     const int q = lane & 3;   // k index inside a k-step (A column / B row)
     const int r = lane >> 2;  // row of the 8x8 fragment (cell) / B column
-    const long long cell = (long long)blockIdx.x * kCellsPerCta + warp * 8 + r;
-    const double2 cxy = args.cell_xy[cell];
+    const long long cell = (long long)(args.cell_tile0 + ct_local) * kCellsPerCta + warp * 8 + r;
+    const double* wsrc = args.wfrag + (size_t)ct_local * n_stages * kWStageDoubles + threadIdx.x;
 
     double acc[2 * NP][2];
     double accm[MASKED ? 2 * NP : 1][2];
@@ -244,55 +310,34 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
             accm[i][1] = 0.0;
         }
     }
-    double wsum = 0.0;
 
-    double w_cur[kKT / 4];
+    double w_cur[kKSteps];
 #pragma unroll
-    for (int kk = 0; kk < kKT / 4; kk++) {
-        const double2 s = args.st_xy[kk * 4 + q];
-        const double dx = cxy.x - s.x, dy = cxy.y - s.y;
-        w_cur[kk] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp);
-    }
-
-    // de-phase the two warps that share an SM sub-partition (warp w and w+4): the late one runs its
-    // DMMAs while the early one is in its per-stage non-DMMA gap (barrier wait, first LDS, release)
-    if (warp >= kConsumerWarps / 2 && args.stagger_cycles > 0) {
-        const long long t_start = clock64();
-        while (clock64() - t_start < args.stagger_cycles) {
-        }
-    }
+    for (int kk = 0; kk < kKSteps; kk++) w_cur[kk] = __ldcs(wsrc + kk * kThreads);
 
     for (int it = 0; it < n_stages; it++) {
         const int slot = it % kStages;
         const int j = it / kStages;
-        const unsigned char* stage = smem + slot * L::kStageBytes;
-        const double* zs = reinterpret_cast<const double*>(stage);
-        const double2* cs = reinterpret_cast<const double2*>(zs + kBlkCoordOff);
-        if (!(DBG & 2) || it < kStages) mbar_wait(&full_bar[slot], j & 1);
+        const double* zs = reinterpret_cast<const double*>(smem + slot * L::kStageBytes);
 
-        double w_next[kKT / 4];
+        // A fragments of the next stage: in flight underneath this stage's DMMAs
+        double w_next[kKSteps];
+        {
+            const int itn = (it + 1 < n_stages) ? it + 1 : it;
+            const double* wn = wsrc + (size_t)itn * kWStageDoubles;
 #pragma unroll
-        for (int kk = 0; kk < kKT / 4; kk++) {
-            if (DBG & 4) {
-                w_next[kk] = w_cur[kk] + 1e-9;
-                continue;
-            }
-            const double2 s = cs[kk * 4 + q];
-            const double dx = cxy.x - s.x, dy = cxy.y - s.y;
-            w_next[kk] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp);
+            for (int kk = 0; kk < kKSteps; kk++) w_next[kk] = __ldcs(wn + kk * kThreads);
         }
+        mbar_wait(&full_bar[slot], j & 1);
 #pragma unroll
-        for (int kk = 0; kk < kKT / 4; kk++) {
+        for (int kk = 0; kk < kKSteps; kk++) {
             const double a = w_cur[kk];
-            wsum += a;
             const double* zrow = zs + (kk * 4 + q) * kGranLd + 2 * r;
             const double* mrow = zrow + kBlkDoubles;  // mask granule block follows the z0 block
 #pragma unroll
             for (int i = 0; i < NP; i++) {
-                double2 b;
                 // column group i lives in granule block i/8 (256-date tiles span two blocks)
-                if (DBG & 1) b = make_double2(a, a);
-                else b = *reinterpret_cast<const double2*>(zrow + (i >> 3) * kBlkDoubles + 16 * (i & 7));
+                const double2 b = *reinterpret_cast<const double2*>(zrow + (i >> 3) * kBlkDoubles + 16 * (i & 7));
                 dmma884(acc[2 * i][0], acc[2 * i][1], a, b.x);
                 dmma884(acc[2 * i + 1][0], acc[2 * i + 1][1], a, b.y);
                 if (MASKED) {
@@ -309,20 +354,17 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
             if (atomicAdd(&release_cnt[slot], 1) == kConsumerWarps - 1) {
                 release_cnt[slot] = 0;
                 __threadfence_block();
-                if (!(DBG & 2) && it + kStages < n_stages)
-                    produce_stage<NP, MASKED>(args, smem, full_bar, it + kStages, n_stages, gran0);
+                if (it + kStages < n_stages) produce_stage<NP, MASKED>(args, smem, full_bar, it + kStages, gran0);
             }
         }
 #pragma unroll
-        for (int kk = 0; kk < kKT / 4; kk++) w_cur[kk] = w_next[kk];
+        for (int kk = 0; kk < kKSteps; kk++) w_cur[kk] = w_next[kk];
     }
 
     // ===== epilogue: normalise, NA rule, per-date early-outs, store =====
-    // lanes of a quad share the cell row; their partial weight sums cover disjoint stations
-    wsum += __shfl_xor_sync(0xffffffffu, wsum, 1);
-    wsum += __shfl_xor_sync(0xffffffffu, wsum, 2);
     const double na = __longlong_as_double((long long)kNaRealBits);
     if (cell >= args.n_cells) return;
+    const double wsum = args.wsum[cell];
     const double inv_wsum = 1.0 / wsum;
 #pragma unroll
     for (int i = 0; i < NP; i++) {
@@ -340,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
             double v = MASKED ? numer / denom : numer * inv_wsum;
             // R/IDW.R:332,339 ; R/Cressman.R:317 : !is.finite(v) | denom == 0 -> NA
             if (!isfinite(v) || denom == 0.0) v = na;
-            if (WMODE != kCressman) {
+            if (args.date_flag != nullptr) {
                 const uint8_t fl = args.date_flag[t];
                 if (fl == 1) v = na;        // R/IDW.R:299-301 all-NA date
                 else if (fl == 2) v = 0.0;  // R/IDW.R:294-297 all |obs| < 1e-12
@@ -390,22 +432,6 @@ __global__ void prep_obs_kernel(const double* __restrict__ obs, long long ld_obs
         date_flag[t] = (c == 0) ? 1 : (b ? 0 : 2);
         date_has_na[t] = (c < n_st) ? 1 : 0;
     }
-}
-
-// writes the station coordinates of stage+1 into the tail of every granule block (once per plan)
-__global__ void fill_block_coords_kernel(const double2* __restrict__ st_xy, double* __restrict__ z0,
-                                         double* __restrict__ mask, int n_stages, int n_gran) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = n_gran * n_stages * kKT;
-    if (idx >= total) return;
-    const int k = idx % kKT;
-    const int blk = idx / kKT;            // g * n_stages + stage
-    const int stage = blk % n_stages;
-    const double2 c = st_xy[(stage + 1) * kKT + k];
-    double2* dz = reinterpret_cast<double2*>(z0 + (size_t)blk * kBlkDoubles + kBlkCoordOff);
-    double2* dm = reinterpret_cast<double2*>(mask + (size_t)blk * kBlkDoubles + kBlkCoordOff);
-    dz[k] = c;
-    dm[k] = c;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -139,6 +139,10 @@ class Plan:
         _native.check(self._lib.ipr_plan_cressman(self._h, rad.ctypes.data, rad.shape[0], t0, t1, C.c_void_p(d_out),
                                                   ld_out, stack_stride, err, _native.ERRLEN), err)
 
+    def reset_cache(self):
+        """Forget the cached A operand (weights) so that the next call regenerates it."""
+        self._lib.ipr_plan_reset_cache(self._h)
+
     def sync(self):
         if self._lib.ipr_plan_sync(self._h) != 0:
             raise _native.NativeError(-2, "stream synchronisation failed")

@@ -10,12 +10,13 @@ cx, cy, sx, sy, obs = synthetic.synthetic_case(ncol, nrow, S, D)
 C = cx.size
 plan = engine.Plan(0, cx, cy, sx, sy, D)
 plan.set_obs(obs)
-tag = os.environ.get("IPR_STAGGER_CYCLES", "default")
+tag = os.environ.get("IPR_WCACHE_MB", "all")
 def run(name, fn, flops, reps=3):
     best = 1e9
     for _ in range(reps):
+        if os.environ.get("IPR_REGEN"): plan.reset_cache()
         plan.timer_start(); fn(); best = min(best, plan.timer_stop())
-    print(f"[stagger={tag}] {name}: {best:.2f} ms {C*D/best*1e-6:.3f} Gcd/s {flops/best*1e-9:.2f} TF ({flops/best*1e-9/37.12*100:.1f}%)", flush=True)
+    print(f"[wcache={tag}] {name}: {best:.2f} ms {C*D/best*1e-6:.3f} Gcd/s {flops/best*1e-9:.2f} TF ({flops/best*1e-9/37.12*100:.1f}%)", flush=True)
 if "idw" in which:
     out = torch.empty((D, C), dtype=torch.float64, device="cuda")
     run("IDW", lambda: plan.idw(out.data_ptr(), 2.0), 2.0*C*S*D)
