@@ -205,6 +205,37 @@ def test_plan_api_equals_one_shot_and_date_shards_agree():
         assert np.array_equal(multi, ref_out, equal_nan=True)
 
 
+def test_weight_cache_chunking_and_reset(monkeypatch):
+    """The A-operand cache is chunked over cell tiles when it does not fit its memory budget; the
+    result must not depend on the chunking, nor on whether the cache is reused or regenerated."""
+    import torch
+
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(70, 41, 130, 300, na_frac=0.01, plant_zero_dist=3, seed=13)
+    want = engine.idw_grid(cx, cy, sx, sy, obs, p=2.0)
+    assert_parity(want, ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="unchunked")
+    monkeypatch.setenv("IPR_WCACHE_MB", "1")          # 1 MiB -> a few cell tiles per chunk
+    got = engine.idw_grid(cx, cy, sx, sy, obs, p=2.0)
+    assert np.array_equal(got, want, equal_nan=True)
+    radii = np.array([5e3, 20e3])
+    c1 = engine.cressman_grid(cx, cy, sx, sy, obs, radii)
+    monkeypatch.delenv("IPR_WCACHE_MB")
+    c2 = engine.cressman_grid(cx, cy, sx, sy, obs, radii)
+    assert np.array_equal(c1, c2, equal_nan=True)
+    # cached vs regenerated weights, and switching weight functions on one plan
+    plan = engine.Plan(0, cx, cy, sx, sy, 300)
+    plan.set_obs(obs)
+    o = torch.empty((3, 300, cx.size), dtype=torch.float64, device="cuda")
+    plan.idw(o[0].data_ptr(), 2.0)
+    plan.idw(o[1].data_ptr(), 3.0)
+    plan.reset_cache()
+    plan.idw(o[2].data_ptr(), 2.0)
+    plan.sync()
+    assert np.array_equal(o[0].cpu().numpy(), o[2].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(o[0].cpu().numpy().T, want, equal_nan=True)
+    assert_parity(o[1].cpu().numpy().T, ref.idw_reference(cx, cy, sx, sy, obs, 3.0), label="p=3 after p=2")
+    plan.close()
+
+
 def test_error_paths_report_messages():
     lib = _native.load()
     cx, cy, sx, sy, obs = synthetic.synthetic_case(4, 4, 5, 3)
