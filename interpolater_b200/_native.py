@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "ipr_plan_create", "ipr_plan_destroy", "ipr_plan_set_obs", "ipr_plan_set_obs_device",
     "ipr_plan_idw", "ipr_plan_cressman", "ipr_plan_sync", "ipr_plan_reset_cache",
     "ipr_plan_timer_start", "ipr_plan_timer_stop", "ipr_plan_launch_count", "ipr_plan_zero_pairs",
+    "ipr_plan_stage_blocks",
     "ipr_plan_stream", "ipr_host_alloc", "ipr_host_free",
 ]
 
@@ -85,6 +86,8 @@ def load() -> C.CDLL:
     lib.ipr_plan_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.ipr_plan_launch_count.restype = C.c_int64
     lib.ipr_plan_launch_count.argtypes = [vp]
+    lib.ipr_plan_stage_blocks.restype = C.c_int
+    lib.ipr_plan_stage_blocks.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.ipr_plan_zero_pairs.restype = C.c_int64
     lib.ipr_plan_zero_pairs.argtypes = [vp]
     lib.ipr_plan_stream.restype = vp

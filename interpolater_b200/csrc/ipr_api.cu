@@ -4,6 +4,7 @@
 #include "../../include/interpolater_b200.h"
 
 #include <algorithm>
+#include <utility>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -40,6 +41,34 @@ void set_err(char* err, size_t errlen, const char* fmt, ...) {
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 inline double canon_zero(double v) { return v == 0.0 ? 0.0 : v; }  // -0 -> +0
 
+// Z-order (Morton) sort of points on a 65536^2 lattice spanning their bounding box
+std::vector<int> morton_order(const double* x, const double* y, int n) {
+    double x0 = x[0], x1 = x[0], y0 = y[0], y1 = y[0];
+    for (int i = 1; i < n; i++) {
+        x0 = std::min(x0, x[i]); x1 = std::max(x1, x[i]);
+        y0 = std::min(y0, y[i]); y1 = std::max(y1, y[i]);
+    }
+    const double span = std::max(std::max(x1 - x0, y1 - y0), 1e-300);
+    auto spread = [](uint32_t v) {
+        uint64_t r = v & 0xFFFF;
+        r = (r | (r << 8)) & 0x00FF00FF;
+        r = (r | (r << 4)) & 0x0F0F0F0F;
+        r = (r | (r << 2)) & 0x33333333;
+        r = (r | (r << 1)) & 0x55555555;
+        return r;
+    };
+    std::vector<std::pair<uint64_t, int>> key(n);
+    for (int i = 0; i < n; i++) {
+        const uint32_t ix = (uint32_t)std::min(65535.0, (x[i] - x0) / span * 65535.0);
+        const uint32_t iy = (uint32_t)std::min(65535.0, (y[i] - y0) / span * 65535.0);
+        key[i] = {spread(ix) | (spread(iy) << 1), i};
+    }
+    std::sort(key.begin(), key.end());
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; i++) perm[i] = key[i].second;
+    return perm;
+}
+
 }  // namespace
 
 struct ipr_plan {
@@ -71,6 +100,11 @@ struct ipr_plan {
     // A-operand cache (weights in DMMA fragment order) for a chunk of cell tiles + per-cell sums
     double* d_wfrag = nullptr;
     double* d_wsum = nullptr;
+    int* d_stage_list = nullptr;  // per cell tile of the chunk: stages with any non-zero weight
+    int* d_n_active = nullptr;
+    int* d_perm = nullptr;        // spatial (Morton) order of the stations: sorted position -> input index
+    unsigned long long* d_active_total = nullptr;
+    unsigned long long stage_tiles_total = 0;  // (cell tile, stage) blocks the dense product would visit
     int w_chunk_tiles = 0;   // capacity of d_wfrag in cell tiles
     int w_mode = -1;         // what the cache currently holds: weight mode, parameter, first tile
     double w_param = 0.0;
@@ -113,6 +147,10 @@ int ensure_weights(ipr_plan* p, int mode, const WeightParams& wp, int tile0, int
     w.st_xy = p->d_st;
     w.wfrag = p->d_wfrag;
     w.wsum = p->d_wsum;
+    w.stage_list = p->d_stage_list;
+    w.n_active = p->d_n_active;
+    w.active_total = p->d_active_total;
+    p->stage_tiles_total += (unsigned long long)n_tiles * p->n_stages;
     w.cell_tile0 = tile0;
     w.n_cell_tiles = n_tiles;
     w.n_stages = p->n_stages;
@@ -147,6 +185,8 @@ int ensure_wcache(ipr_plan* p, char* err, size_t errlen) {
         return IPR_ENOMEM;
     }
     IPR_CUDA(cudaMalloc(&p->d_wfrag, tile_bytes * tiles));
+    IPR_CUDA(cudaMalloc(&p->d_stage_list, sizeof(int) * (size_t)tiles * p->n_stages));
+    IPR_CUDA(cudaMalloc(&p->d_n_active, sizeof(int) * (size_t)tiles));
     p->w_chunk_tiles = (int)tiles;
     return IPR_OK;
 }
@@ -165,6 +205,8 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
         ContractArgs a{};
         a.wfrag = p->d_wfrag;
         a.wsum = p->d_wsum;
+        a.stage_list = p->d_stage_list;
+        a.n_active = p->d_n_active;
         a.z0 = p->d_z0;
         a.mask = p->d_mask;
         a.date_flag = idw ? p->d_flag : nullptr;
@@ -236,7 +278,7 @@ int scan_zero_pairs(ipr_plan* p, char* err, size_t errlen) {
     IPR_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(int), p->stream));
     const int threads = 256;
     const unsigned blocks = (unsigned)((p->n_cells + threads - 1) / threads);
-    zero_pairs_kernel<<<blocks, threads, 0, p->stream>>>(p->d_cell, p->n_cells, p->d_st, p->n_st, p->d_pairs,
+    zero_pairs_kernel<<<blocks, threads, 0, p->stream>>>(p->d_cell, p->n_cells, p->d_st, p->n_st, p->d_perm, p->d_pairs,
                                                          p->pair_capacity, p->d_counters);
     IPR_CUDA(cudaGetLastError());
     p->launches++;
@@ -280,7 +322,7 @@ int prepare_obs(ipr_plan* p, char* err, size_t errlen) {
     IPR_CUDA(cudaMemsetAsync(p->d_counters + 1, 0, sizeof(int), p->stream));
     dim3 block(32, 8);
     dim3 grid((unsigned)((p->n_dates + 31) / 32));
-    prep_obs_kernel<<<grid, block, 0, p->stream>>>(p->d_obs, p->n_dates, p->n_dates, p->n_st, p->d_z0, p->d_mask,
+    prep_obs_kernel<<<grid, block, 0, p->stream>>>(p->d_obs, p->n_dates, p->n_dates, p->n_st, p->d_perm, p->d_z0, p->d_mask,
                                                    p->n_stages, p->d_flag, p->d_has_na, p->d_counters + 1);
     IPR_CUDA(cudaGetLastError());
     p->launches++;
@@ -390,6 +432,9 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     PLAN_CUDA(cudaMalloc(&p->d_counters, sizeof(int) * 4));
     PLAN_CUDA(cudaMalloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
     PLAN_CUDA(cudaMalloc(&p->d_wsum, sizeof(double) * p->c_pad));
+    PLAN_CUDA(cudaMalloc(&p->d_perm, sizeof(int) * n_st));
+    PLAN_CUDA(cudaMalloc(&p->d_active_total, sizeof(unsigned long long)));
+    PLAN_CUDA(cudaMemsetAsync(p->d_active_total, 0, sizeof(unsigned long long), p->stream));
     PLAN_CUDA(cudaMemsetAsync(p->d_z0, 0, sizeof(double) * p->z_doubles, p->stream));
     PLAN_CUDA(cudaMemsetAsync(p->d_mask, 0, sizeof(double) * p->z_doubles, p->stream));
     PLAN_CUDA(cudaMemsetAsync(p->d_flag, 0, (size_t)p->n_gran * kGran, p->stream));
@@ -406,15 +451,20 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
             }
         }
         PLAN_CUDA(cudaMemcpyAsync(p->d_cell, h.data(), sizeof(double2) * p->c_pad, cudaMemcpyHostToDevice, p->stream));
-        std::vector<double2> hs(p->s_pad + kKT, make_double2(kPadCoord, kPadCoord));
         for (int i = 0; i < n_st; i++) {
-            hs[i] = make_double2(canon_zero(st_x[i]), canon_zero(st_y[i]));
-            if (!std::isfinite(hs[i].x) || !std::isfinite(hs[i].y)) {
+            if (!std::isfinite(st_x[i]) || !std::isfinite(st_y[i])) {
                 ipr_plan_destroy(p);
                 set_err(err, errlen, "station coordinate %d is not finite", i);
                 return IPR_EINVAL;
             }
         }
+        // stations in Morton order: a pipeline stage (kKT consecutive stations) is then a compact
+        // blob, so that for Cressman most (cell tile, stage) blocks lie wholly beyond the radius and
+        // are skipped.  The permutation only changes the order of summation.
+        std::vector<int> perm = morton_order(st_x, st_y, n_st);
+        std::vector<double2> hs(p->s_pad + kKT, make_double2(kPadCoord, kPadCoord));
+        for (int i = 0; i < n_st; i++) hs[i] = make_double2(canon_zero(st_x[perm[i]]), canon_zero(st_y[perm[i]]));
+        PLAN_CUDA(cudaMemcpyAsync(p->d_perm, perm.data(), sizeof(int) * n_st, cudaMemcpyHostToDevice, p->stream));
         PLAN_CUDA(cudaMemcpyAsync(p->d_st, hs.data(), sizeof(double2) * hs.size(), cudaMemcpyHostToDevice, p->stream));
         PLAN_CUDA(cudaStreamSynchronize(p->stream));  // staging vectors go out of scope
     }
@@ -446,6 +496,10 @@ void ipr_plan_destroy(ipr_plan* p) {
     cudaFree(p->d_fix_st);
     cudaFree(p->d_wfrag);
     cudaFree(p->d_wsum);
+    cudaFree(p->d_stage_list);
+    cudaFree(p->d_n_active);
+    cudaFree(p->d_perm);
+    cudaFree(p->d_active_total);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -536,6 +590,18 @@ int ipr_plan_cressman(ipr_plan* p, const double* radii_m, int32_t n_radii, int32
                                   errlen)))
             return rc;
     }
+    return IPR_OK;
+}
+
+int ipr_plan_stage_blocks(ipr_plan* p, uint64_t* executed, uint64_t* dense) {
+    if (!p || !executed || !dense) return IPR_EINVAL;
+    cudaSetDevice(p->device);
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, p->d_active_total, sizeof v, cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
+        cudaStreamSynchronize(p->stream) != cudaSuccess)
+        return IPR_ECUDA;
+    *executed = v;
+    *dense = p->stage_tiles_total;
     return IPR_OK;
 }
 

@@ -75,6 +75,8 @@ struct TileList {
 struct ContractArgs {
     const double* wfrag;      // A operand cache for cell tiles [cell_tile0, cell_tile0 + n_cell_tiles)
     const double* wsum;       // [c_pad] per-cell sum of weights over all stations
+    const int* stage_list;    // [n_cell_tiles][n_stages] stages holding any non-zero weight, ascending
+    const int* n_active;      // [n_cell_tiles] length of each list
     const double* z0;         // granule blocks [n_gran][n_stages][kBlkDoubles]
     const double* mask;       // same layout (masked variants only)
     const uint8_t* date_flag; // IDW: 0 normal, 1 all-NA layer, 2 exact-zero layer; nullptr for Cressman
@@ -92,6 +94,9 @@ struct WeightArgs {
     const double2* st_xy;     // [s_pad]
     double* wfrag;            // chunk base
     double* wsum;             // [c_pad]
+    int* stage_list;          // [n_cell_tiles][n_stages]
+    int* n_active;            // [n_cell_tiles]
+    unsigned long long* active_total;  // cumulative count of active (cell tile, stage) blocks
     int cell_tile0, n_cell_tiles;
     int n_stages;
     WeightParams wp;
@@ -194,15 +199,15 @@ struct SmemLayout {
 // Refill one pipeline stage: one bulk copy (TMA bulk engine) per granule block.  Called by one lane.
 template <int NP, bool MASKED>
 __device__ __forceinline__ void produce_stage(const ContractArgs& args, unsigned char* smem, uint64_t* full_bar,
-                                              int it, int gran0) {
+                                              int it, int sid, int gran0) {
     using L = SmemLayout<NP, MASKED>;
-    const int slot = it % kStages;
+    const int slot = it % kStages;  // it: position in the tile's active-stage list; sid: the stage
     unsigned char* stage = smem + slot * L::kStageBytes;
     // generic-proxy reads of this slot (all warps, ordered by the release counter) precede the
     // async-proxy writes issued below
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&full_bar[slot], L::kTxBytes);
-    const size_t b0 = ((size_t)gran0 * args.n_stages + it) * kBlkDoubles;
+    const size_t b0 = ((size_t)gran0 * args.n_stages + sid) * kBlkDoubles;
     bulk_g2s(stage, args.z0 + b0, kBlkBytes, &full_bar[slot]);
     if (MASKED) {
         bulk_g2s(stage + kBlkBytes, args.mask + b0, kBlkBytes, &full_bar[slot]);
@@ -216,8 +221,10 @@ __device__ __forceinline__ void produce_stage(const ContractArgs& args, unsigned
 // ---------------------------------------------------------------------------------------------
 template <int WMODE>
 __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args) {
-    constexpr int kChunk = 1024;  // stations staged in shared memory at a time (16 KB)
+    constexpr int kChunkStages = 32;               // stages staged in shared memory at a time
+    constexpr int kChunk = kChunkStages * kKT;     // 1024 stations, 16 KB
     __shared__ double2 s_st[kChunk];
+    __shared__ int s_n_active;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int q = lane & 3;   // station inside the k-step (A column)
@@ -226,36 +233,45 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
     const long long cell = (long long)ct * kCellsPerCta + warp * 8 + r;
     const double2 cxy = args.cell_xy[cell];
     double* dst = args.wfrag + (size_t)blockIdx.x * args.n_stages * kWStageDoubles + threadIdx.x;
-    double wsum0 = 0.0, wsum1 = 0.0, wsum2 = 0.0, wsum3 = 0.0;
-    const int s_pad = args.n_stages * kKT;
-    for (int s0 = 0; s0 < s_pad; s0 += kChunk) {
-        const int n = min(kChunk, s_pad - s0);  // multiple of kKT
+    int* list = args.stage_list + (size_t)blockIdx.x * args.n_stages;
+    double wsum[4] = {0.0, 0.0, 0.0, 0.0};
+    if (threadIdx.x == 0) s_n_active = 0;
+    for (int st0 = 0; st0 < args.n_stages; st0 += kChunkStages) {
+        const int ns = min(kChunkStages, args.n_stages - st0);
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += kThreads) s_st[i] = args.st_xy[s0 + i];
+        for (int i = threadIdx.x; i < ns * kKT; i += kThreads) s_st[i] = args.st_xy[st0 * kKT + i];
         __syncthreads();
-        double* d = dst + (size_t)(s0 / 4) * kThreads;
-        // 4 independent k-steps per iteration: the reciprocal chains overlap
-        for (int ks = 0; ks < n / 4; ks += 4) {
-            double w[4];
+        for (int sl = 0; sl < ns; sl++) {
+            double w[kKSteps];
+            bool any = false;
+            // independent reciprocal chains overlap; fixed summation order per k-step residue
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const double2 s = s_st[(ks + u) * 4 + q];
+            for (int kk = 0; kk < kKSteps; kk++) {
+                const double2 s = s_st[sl * kKT + kk * 4 + q];
                 const double dx = cxy.x - s.x, dy = cxy.y - s.y;
-                w[u] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp);
+                w[kk] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp);
+                wsum[kk & 3] += w[kk];
+                any |= (w[kk] != 0.0);
             }
-            wsum0 += w[0];
-            wsum1 += w[1];
-            wsum2 += w[2];
-            wsum3 += w[3];
+            // a stage whose 64 x kKT weights are all zero (Cressman: every station beyond R) is not
+            // stored and will be skipped by the contraction
+            if (__syncthreads_or(any)) {
+                double* d = dst + (size_t)(st0 + sl) * kWStageDoubles;
 #pragma unroll
-            for (int u = 0; u < 4; u++) __stcs(d + (size_t)(ks + u) * kThreads, w[u]);
+                for (int kk = 0; kk < kKSteps; kk++) __stcs(d + kk * kThreads, w[kk]);
+                if (threadIdx.x == 0) list[s_n_active++] = st0 + sl;
+            }
         }
     }
-    // fixed summation order: ((k-steps 0,4,8..) + (1,5,..)) + ((2,6,..) + (3,7,..)), then the quad
-    double wsum = (wsum0 + wsum1) + (wsum2 + wsum3);
-    wsum += __shfl_xor_sync(0xffffffffu, wsum, 1);
-    wsum += __shfl_xor_sync(0xffffffffu, wsum, 2);
-    if (q == 0) args.wsum[cell] = wsum;
+    double tot = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
+    // lanes of a quad share the cell; their partial sums cover disjoint stations
+    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+    if (q == 0) args.wsum[cell] = tot;
+    if (threadIdx.x == 0) {
+        args.n_active[blockIdx.x] = s_n_active;
+        atomicAdd(args.active_total, (unsigned long long)s_n_active);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -279,7 +295,10 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
     const int ct_local = blockIdx.x / args.tiles.n;
     const int tile_t0 = args.tiles.t0[tile_idx];   // multiple of kGran
     const int gran0 = tile_t0 / kGran;
-    const int n_stages = args.n_stages;
+    // the tile's list of stages with any non-zero weight (all of them for IDW; for Cressman only
+    // the stations near the tile: the rest of the dense product is exactly zero and is skipped)
+    const int* list = args.stage_list + (size_t)ct_local * args.n_stages;
+    const int n_stages = args.n_active[ct_local];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
@@ -291,13 +310,14 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int it = 0; it < kStages && it < n_stages; it++) produce_stage<NP, MASKED>(args, smem, full_bar, it, gran0);
+        for (int it = 0; it < kStages && it < n_stages; it++)
+            produce_stage<NP, MASKED>(args, smem, full_bar, it, __ldg(list + it), gran0);
     }
 
     const int q = lane & 3;   // k index inside a k-step (A column / B row)
     const int r = lane >> 2;  // row of the 8x8 fragment (cell) / B column
     const long long cell = (long long)(args.cell_tile0 + ct_local) * kCellsPerCta + warp * 8 + r;
-    const double* wsrc = args.wfrag + (size_t)ct_local * n_stages * kWStageDoubles + threadIdx.x;
+    const double* wsrc = args.wfrag + (size_t)ct_local * args.n_stages * kWStageDoubles + threadIdx.x;
 
     double acc[2 * NP][2];
     double accm[MASKED ? 2 * NP : 1][2];
@@ -312,8 +332,11 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
     }
 
     double w_cur[kKSteps];
+    if (n_stages > 0) {
+        const double* w0 = wsrc + (size_t)__ldg(list) * kWStageDoubles;
 #pragma unroll
-    for (int kk = 0; kk < kKSteps; kk++) w_cur[kk] = __ldcs(wsrc + kk * kThreads);
+        for (int kk = 0; kk < kKSteps; kk++) w_cur[kk] = __ldcs(w0 + kk * kThreads);
+    }
 
     for (int it = 0; it < n_stages; it++) {
         const int slot = it % kStages;
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
         double w_next[kKSteps];
         {
             const int itn = (it + 1 < n_stages) ? it + 1 : it;
-            const double* wn = wsrc + (size_t)itn * kWStageDoubles;
+            const double* wn = wsrc + (size_t)__ldg(list + itn) * kWStageDoubles;
 #pragma unroll
             for (int kk = 0; kk < kKSteps; kk++) w_next[kk] = __ldcs(wn + kk * kThreads);
         }
@@ -354,7 +377,8 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
             if (atomicAdd(&release_cnt[slot], 1) == kConsumerWarps - 1) {
                 release_cnt[slot] = 0;
                 __threadfence_block();
-                if (it + kStages < n_stages) produce_stage<NP, MASKED>(args, smem, full_bar, it + kStages, gran0);
+                if (it + kStages < n_stages)
+                    produce_stage<NP, MASKED>(args, smem, full_bar, it + kStages, __ldg(list + it + kStages), gran0);
             }
         }
 #pragma unroll
@@ -397,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
 //   block = (32 dates, 8 station stripes)
 // ---------------------------------------------------------------------------------------------
 __global__ void prep_obs_kernel(const double* __restrict__ obs, long long ld_obs, int n_dates, int n_st,
-                                double* __restrict__ z0, double* __restrict__ mask, int n_stages,
+                                const int* __restrict__ perm, double* __restrict__ z0, double* __restrict__ mask, int n_stages,
                                 uint8_t* __restrict__ date_flag, uint8_t* __restrict__ date_has_na,
                                 int* __restrict__ nonfinite_count) {
     __shared__ int s_cnt[8][32];
@@ -407,7 +431,8 @@ __global__ void prep_obs_kernel(const double* __restrict__ obs, long long ld_obs
     if (t < n_dates) {
         const size_t gbase = (size_t)(t / kGran) * n_stages * kBlkDoubles + (t % kGran);
         for (int s = threadIdx.y; s < n_st; s += 8) {
-            const double v = obs[(long long)s * ld_obs + t];
+            // row s of the B operand is the station that the spatial sort put at position s
+            const double v = obs[(long long)perm[s] * ld_obs + t];
             const bool isna = (v != v);
             const size_t off = gbase + (size_t)(s / kKT) * kBlkDoubles + (s % kKT) * kGranLd;
             z0[off] = isna ? 0.0 : v;
@@ -439,7 +464,8 @@ __global__ void prep_obs_kernel(const double* __restrict__ obs, long long ld_obs
 // canonicalised to +0 on upload), one thread per cell, stations broadcast from shared memory.
 // ---------------------------------------------------------------------------------------------
 __global__ void zero_pairs_kernel(const double2* __restrict__ cell_xy, long long n_cells,
-                                  const double2* __restrict__ st_xy, int n_st, int2* __restrict__ pairs,
+                                  const double2* __restrict__ st_xy, int n_st, const int* __restrict__ perm,
+                                  int2* __restrict__ pairs,
                                   int capacity, int* __restrict__ n_pairs) {
     __shared__ double2 s_st[256];
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,7 +482,7 @@ __global__ void zero_pairs_kernel(const double2* __restrict__ cell_xy, long long
                 const double2 s = s_st[k];
                 if (__double_as_longlong(s.x) == cxb && __double_as_longlong(s.y) == cyb) {
                     const int slot = atomicAdd(n_pairs, 1);
-                    if (slot < capacity) pairs[slot] = make_int2((int)c, s0 + k);
+                    if (slot < capacity) pairs[slot] = make_int2((int)c, perm[s0 + k]);  // original station index
                 }
             }
         }

@@ -160,6 +160,13 @@ class Plan:
     def launch_count(self) -> int:
         return int(self._lib.ipr_plan_launch_count(self._h))
 
+    def stage_blocks(self):
+        """(executed, dense) cumulative counts of A-operand blocks (see ipr_plan_stage_blocks)."""
+        ex, de = C.c_uint64(), C.c_uint64()
+        if self._lib.ipr_plan_stage_blocks(self._h, C.byref(ex), C.byref(de)) != 0:
+            raise _native.NativeError(-2, "stage block query failed")
+        return int(ex.value), int(de.value)
+
     @property
     def zero_pairs(self) -> int:
         return int(self._lib.ipr_plan_zero_pairs(self._h))

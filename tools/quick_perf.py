@@ -28,3 +28,5 @@ if "masked" in which:
     plan.set_obs(obs3)
     out = torch.empty((D, C), dtype=torch.float64, device="cuda")
     run("IDW-masked", lambda: plan.idw(out.data_ptr(), 2.0), 4.0*C*S*D, 2)
+ex, de = plan.stage_blocks()
+print(f"stage blocks executed/dense = {ex}/{de} = {ex/max(de,1):.3f}")
