@@ -4,6 +4,7 @@
 #include "../../include/interpolater_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <utility>
 #include <cmath>
 #include <cstdarg>
@@ -653,8 +654,21 @@ struct HostJob {
 
 constexpr int kRing = 3;
 
+// IPR_TRACE=1: phase timestamps of the host-buffer path on stderr
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(getenv("IPR_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[ipr trace] %8.2f ms  %s\n", ms, what);
+    }
+};
+
 int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, size_t errlen) {
     if (d0 >= d1) return IPR_OK;
+    Trace tr;
     const int nd = d1 - d0;
     ipr_plan* plan = nullptr;
     int rc = ipr_plan_create(&plan, device, job.cell_x, job.cell_y, job.n_cells, job.st_x, job.st_y, job.n_st, nd, err,
@@ -679,44 +693,57 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
             ipr_plan_destroy(p);
         }
     } g{plan};
+    tr.mark("plan created (allocations, coordinate upload, zero-distance scan)");
     rc = plan_set_obs_ld(plan, job.obs + d0, job.n_dates, err, errlen);
     if (rc) return rc;
+    tr.mark("obs uploaded and prepared");
     const int n_stacks = job.cressman ? job.n_radii : 1;
-    // chunk: up to 256 dates, bounded so that one ring slot stays <= ~2 GiB per stack set
-    long long chunk = 256;
-    const long long bytes_per_date = (long long)job.n_cells * 8 * n_stacks;
-    while (chunk > 16 && chunk * bytes_per_date > (3LL << 30)) chunk /= 2;
-    chunk = std::min<long long>(chunk, round_up(nd, 16));
-    const long long stack_stride = (long long)job.n_cells * chunk;
+    // Work items: (stack, date chunk), stack outermost so that the A-operand cache is generated once
+    // per radius.  Chunks are whole 128-date granules (256 dates, or 128 when a slot would exceed
+    // ~3 GiB); the first chunk of the block is a single granule so that D2H starts early.
+    const long long gran_bytes = (long long)job.n_cells * 8 * kGran;
+    const int chunk = (2 * gran_bytes > (3LL << 30)) ? kGran : 2 * kGran;
+    struct Item { int stack, t0, t1; };
+    std::vector<Item> items;
+    for (int s = 0; s < n_stacks; s++) {
+        int t = 0;
+        while (t < nd) {
+            const int len = (s == 0 && t == 0) ? kGran : chunk;
+            items.push_back({s, t, std::min(nd, t + len)});
+            t += len;
+        }
+    }
+    const size_t slot_doubles = (size_t)job.n_cells * std::min(chunk, (int)round_up(nd, 16));
     IPR_CUDA(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
-    const int n_chunks = (int)((nd + chunk - 1) / chunk);
-    const int n_ring = std::min(kRing, n_chunks);
+    const int n_ring = std::min<int>(kRing, (int)items.size());
     for (int i = 0; i < n_ring; i++) {
-        IPR_CUDA(cudaMalloc(&g.ring[i], sizeof(double) * stack_stride * n_stacks));
+        IPR_CUDA(cudaMalloc(&g.ring[i], sizeof(double) * slot_doubles));
         IPR_CUDA(cudaEventCreateWithFlags(&g.done[i], cudaEventDisableTiming));
         IPR_CUDA(cudaEventCreateWithFlags(&g.computed[i], cudaEventDisableTiming));
     }
-    for (int ci = 0; ci < n_chunks; ci++) {
-        const int slot = ci % n_ring;
-        const int t0 = (int)(ci * chunk), t1 = (int)std::min<long long>(nd, t0 + chunk);
-        if (ci >= n_ring) IPR_CUDA(cudaStreamWaitEvent(plan->stream, g.done[slot], 0));
+    tr.mark("ring allocated");
+    for (size_t ii = 0; ii < items.size(); ii++) {
+        const Item& it = items[ii];
+        const int slot = (int)(ii % n_ring);
+        if ((int)ii >= n_ring) IPR_CUDA(cudaStreamWaitEvent(plan->stream, g.done[slot], 0));
         if (job.cressman)
-            rc = ipr_plan_cressman(plan, job.radii, job.n_radii, t0, t1, g.ring[slot], job.n_cells, stack_stride, err,
+            rc = ipr_plan_cressman(plan, job.radii + it.stack, 1, it.t0, it.t1, g.ring[slot], job.n_cells, 0, err,
                                    errlen);
         else
-            rc = ipr_plan_idw(plan, job.p, t0, t1, g.ring[slot], job.n_cells, err, errlen);
+            rc = ipr_plan_idw(plan, job.p, it.t0, it.t1, g.ring[slot], job.n_cells, err, errlen);
         if (rc) return rc;
         IPR_CUDA(cudaEventRecord(g.computed[slot], plan->stream));
         IPR_CUDA(cudaStreamWaitEvent(g.copy, g.computed[slot], 0));
-        for (int s = 0; s < n_stacks; s++) {
-            double* dst = job.out + (size_t)s * job.n_cells * job.n_dates + (size_t)(d0 + t0) * job.n_cells;
-            IPR_CUDA(cudaMemcpyAsync(dst, g.ring[slot] + (size_t)s * stack_stride,
-                                     sizeof(double) * (size_t)job.n_cells * (t1 - t0), cudaMemcpyDeviceToHost, g.copy));
-        }
+        double* dst = job.out + (size_t)it.stack * job.n_cells * job.n_dates + (size_t)(d0 + it.t0) * job.n_cells;
+        IPR_CUDA(cudaMemcpyAsync(dst, g.ring[slot], sizeof(double) * (size_t)job.n_cells * (it.t1 - it.t0),
+                                 cudaMemcpyDeviceToHost, g.copy));
         IPR_CUDA(cudaEventRecord(g.done[slot], g.copy));
     }
+    tr.mark("all chunks submitted");
     IPR_CUDA(cudaStreamSynchronize(plan->stream));
+    tr.mark("compute stream drained");
     IPR_CUDA(cudaStreamSynchronize(g.copy));
+    tr.mark("copy stream drained");
     return IPR_OK;
 }
 

@@ -180,6 +180,39 @@ def test_packaged_cressman_cfg2(packaged, packaged_golden, tmp_path, monkeypatch
     assert out["Ensamble"]["10 km"].nlyr() == 60 and out["Validation"]["10 km"]["ID"].tolist() == ["M004", "M005"]
 
 
+def test_synthetic_masked_holdout_validation_cfg5_twin():
+    """Small-scale twin of BASELINE.json configs[4]: 20 % per-date NA, 20 % of the stations held out
+    and passed as stat_validation; raster and validation table through the drop-in signature."""
+    import pandas as pd
+
+    ncol, nrow, n_st, n_dates = 40, 30, 60, 140
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(ncol, nrow, n_st, n_dates, na_frac=0.2, seed=77)
+    names = [f"S{i:03d}" for i in range(n_st)]
+    dates = pd.date_range("2001-01-01", periods=n_dates, freq="D")
+    BD_Obs = pd.DataFrame({"Date": dates, **{nm: obs[:, i] for i, nm in enumerate(names)}})
+    BD_Coord = pd.DataFrame({"Cod": names, "X": sx, "Y": sy, "Z": 0.0})
+    held = [names[i] for i in np.random.default_rng(20260104).choice(n_st, n_st // 5, replace=False)]
+    shp = ipr.SpatVector.from_bbox(200000.0, 200000.0 + ncol * 1000.0, 9000000.0, 9000000.0 + nrow * 1000.0)
+    out = ipr.IDW(BD_Obs, BD_Coord, shp, grid_resolution=1, p=2, Mask=False, n_round=1, stat_validation=held)
+    train = sorted(n for n in names if n not in held)            # IDW feeds stations Cod-sorted
+    ti = [names.index(n) for n in train]
+    want = ref.idw_reference(cx, cy, sx[ti], sy[ti], obs[:, ti], 2.0)
+    want_r = np.array([[ref.r_round(v, 1) for v in row] for row in want])
+    got = out["Ensamble"].values
+    # rounding to 1 digit can flip on values within 1e-13 of a tie: allow no more than a handful
+    diff = ~(np.isclose(got, want_r, rtol=0, atol=1e-12) | (np.isnan(got) & np.isnan(want_r)))
+    assert diff.sum() <= 2
+    grid = ref.grid_from_extent(200000.0, 200000.0 + ncol * 1000.0, 9000000.0, 9000000.0 + nrow * 1000.0, 1000.0)
+    hi = [names.index(n) for n in names if n in held]           # test_data keeps BD_Obs column order
+    wv = ref.validate_reference(grid, got, sx[hi], sy[hi], obs[:, hi])
+    tab = out["Validation"]
+    assert tab["ID"].tolist() == [names[i] for i in hi]
+    for j, row in enumerate(wv):
+        for k in ref.GOF_COLUMNS:
+            a, b = float(tab[k].iloc[j]), row["gof"][k]
+            assert (np.isnan(a) and np.isnan(b)) or a == b, (j, k, a, b)
+
+
 # ---------------------------------------------------------------- plan API / sharding / errors
 def test_plan_api_equals_one_shot_and_date_shards_agree():
     import torch
