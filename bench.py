@@ -409,12 +409,26 @@ def run_ours(a):
                                          ob.ctypes.data, t1 - t0, 2.0, dev, 1, hptr, err, _native.ERRLEN)
                 _native.check(rc, err)
 
+        # PCIe D2H probe on this box right now (1 GiB from the same pinned buffer): the floor of e2e
+        probe = torch.empty(1 << 27, dtype=torch.float64, device="cuda")
+        probe_h = torch.empty(1 << 27, dtype=torch.float64, pin_memory=True)
+        d2h_gbs = 0.0
+        for _ in range(3):
+            torch.cuda.synchronize()
+            tp = time.perf_counter()
+            probe_h.copy_(probe, non_blocking=True)
+            torch.cuda.synchronize()
+            d2h_gbs = max(d2h_gbs, probe.numel() * 8 / (time.perf_counter() - tp) * 1e-9)
+        del probe, probe_h
         for _ in range(min(a.warmup, 2)):
             e2e_step()
         barrier()
+        step_s = []
         t0 = time.perf_counter()
         for _ in range(a.steps):
+            ts = time.perf_counter()
             e2e_step()
+            step_s.append(time.perf_counter() - ts)
         torch.cuda.synchronize()
         sec = (time.perf_counter() - t0) / a.steps
         barrier()
@@ -429,6 +443,9 @@ def run_ours(a):
             "api": "ipr_cressman_f64" if a.workload == "cressman" else "ipr_idw_f64",
             "host_buffers": "pinned (ipr_host_alloc), caller-owned",
             "calls_per_step": n_chunks,
+            "ms_per_step_min_rank0": min(step_s) * 1e3,
+            "pcie_d2h_gbs_probe": d2h_gbs,
+            "pcie_floor_ms": bytes_out / (d2h_gbs * 1e9) * 1e3 if d2h_gbs > 0 else None,
             "checksum_first_1M": checksum,
         }
         lib.ipr_host_free(hptr)

@@ -118,6 +118,11 @@ int64_t ipr_plan_zero_pairs(const ipr_plan* plan);
 /* raw cudaStream_t of the plan (as void*) so a host framework can order its own work */
 void* ipr_plan_stream(const ipr_plan* plan);
 
+/* The library keeps freed multi-MB device work buffers for reuse by later calls (cudaMalloc/cudaFree
+ * of the 16 GB weight cache and the output ring cost up to hundreds of ms per call); this returns
+ * them to the driver.  IPR_POOL_MAX_GB (default 64) bounds what is kept. */
+void ipr_release_cached_memory(void);
+
 /* pinned host memory helpers for callers that want zero-copy-staging D2H (the benchmark) */
 void* ipr_host_alloc(size_t bytes);
 void ipr_host_free(void* p);

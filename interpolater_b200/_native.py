@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "ipr_plan_idw", "ipr_plan_cressman", "ipr_plan_sync", "ipr_plan_reset_cache",
     "ipr_plan_timer_start", "ipr_plan_timer_stop", "ipr_plan_launch_count", "ipr_plan_zero_pairs",
     "ipr_plan_stage_blocks",
-    "ipr_plan_stream", "ipr_host_alloc", "ipr_host_free",
+    "ipr_plan_stream", "ipr_host_alloc", "ipr_host_free", "ipr_release_cached_memory",
 ]
 
 
@@ -92,6 +92,8 @@ def load() -> C.CDLL:
     lib.ipr_plan_zero_pairs.argtypes = [vp]
     lib.ipr_plan_stream.restype = vp
     lib.ipr_plan_stream.argtypes = [vp]
+    lib.ipr_release_cached_memory.restype = None
+    lib.ipr_release_cached_memory.argtypes = []
     lib.ipr_host_alloc.restype = vp
     lib.ipr_host_alloc.argtypes = [C.c_size_t]
     lib.ipr_host_free.restype = None

@@ -4,6 +4,8 @@
 #include "../../include/interpolater_b200.h"
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <chrono>
 #include <utility>
 #include <cmath>
@@ -40,6 +42,89 @@ void set_err(char* err, size_t errlen, const char* fmt, ...) {
     } while (0)
 
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------
+// Device buffer pool.  cudaMalloc / cudaFree of the multi-GB work buffers (A-operand cache, output
+// ring, B operand) was measured to cost anything from 15 to 600 ms per host-buffer call depending
+// on the allocator's mood; freed buffers >= 1 MiB are therefore kept per device and reused by
+// exact size.  ipr_release_cached_memory() (or memory pressure) returns them to the driver.
+// ---------------------------------------------------------------------------------------------
+struct DevicePool {
+    std::mutex mu;
+    std::map<void*, std::pair<int, size_t>> live;              // ptr -> (device, bytes)
+    std::multimap<std::pair<int, size_t>, void*> idle;         // (device, bytes) -> ptr
+    size_t idle_bytes = 0;
+    void drain_locked() {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto& kv : idle) {
+            cudaSetDevice(kv.first.first);
+            cudaFree(kv.second);
+        }
+        idle.clear();
+        idle_bytes = 0;
+        cudaSetDevice(cur);
+    }
+};
+DevicePool& pool() {
+    static DevicePool p;
+    return p;
+}
+size_t pool_limit_bytes() {
+    static size_t v = 0;
+    if (!v) {
+        const char* e = getenv("IPR_POOL_MAX_GB");
+        v = (size_t)(e ? atoll(e) : 64) << 30;
+    }
+    return v;
+}
+
+cudaError_t dev_malloc_raw(void** out, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DevicePool& P = pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.idle.find({dev, bytes});
+    if (it != P.idle.end()) {
+        *out = it->second;
+        P.idle_bytes -= bytes;
+        P.idle.erase(it);
+        P.live[*out] = {dev, bytes};
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // give cached buffers back and retry once
+        cudaGetLastError();
+        P.drain_locked();
+        e = cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess) P.live[*out] = {dev, bytes};
+    return e;
+}
+template <class T>
+cudaError_t dev_malloc(T** out, size_t bytes) {
+    return dev_malloc_raw(reinterpret_cast<void**>(out), bytes);
+}
+void dev_free(void* ptr) {
+    if (!ptr) return;
+    DevicePool& P = pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.live.find(ptr);
+    if (it == P.live.end()) {
+        cudaFree(ptr);
+        return;
+    }
+    const int dev = it->second.first;
+    const size_t bytes = it->second.second;
+    P.live.erase(it);
+    if (bytes >= (1u << 20) && P.idle_bytes + bytes <= pool_limit_bytes()) {
+        P.idle.insert({{dev, bytes}, ptr});
+        P.idle_bytes += bytes;
+    } else {
+        cudaFree(ptr);
+    }
+}
+
 inline double canon_zero(double v) { return v == 0.0 ? 0.0 : v; }  // -0 -> +0
 
 // Z-order (Morton) sort of points on a 65536^2 lattice spanning their bounding box
@@ -114,12 +199,16 @@ struct ipr_plan {
 
 namespace {
 
-void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, std::vector<int>& u256, std::vector<int>& u128,
-                 std::vector<int>& m128);
+// date tiles of one launch group: [MASKED][NP] -> start dates
+struct TileSets {
+    std::vector<int> u[9];  // unmasked, NP = 2, 4, 6, 8 used
+    std::vector<int> m[5];  // masked,   NP = 2, 4 used
+};
+void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, TileSets& ts);
 
 template <int NP, bool MASKED>
 int launch_contract(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles, char* err, size_t errlen) {
-    using L = SmemLayout<NP, MASKED>;
+    using L = SmemLayout<MASKED>;
     static bool configured[64] = {false};
     auto kern = contract_kernel<NP, MASKED>;
     if (!configured[p->device & 63]) {
@@ -185,9 +274,9 @@ int ensure_wcache(ipr_plan* p, char* err, size_t errlen) {
         set_err(err, errlen, "not enough device memory for the weight cache (%zu bytes per cell tile)", tile_bytes);
         return IPR_ENOMEM;
     }
-    IPR_CUDA(cudaMalloc(&p->d_wfrag, tile_bytes * tiles));
-    IPR_CUDA(cudaMalloc(&p->d_stage_list, sizeof(int) * (size_t)tiles * p->n_stages));
-    IPR_CUDA(cudaMalloc(&p->d_n_active, sizeof(int) * (size_t)tiles));
+    IPR_CUDA(dev_malloc(&p->d_wfrag, tile_bytes * tiles));
+    IPR_CUDA(dev_malloc(&p->d_stage_list, sizeof(int) * (size_t)tiles * p->n_stages));
+    IPR_CUDA(dev_malloc(&p->d_n_active, sizeof(int) * (size_t)tiles));
     p->w_chunk_tiles = (int)tiles;
     return IPR_OK;
 }
@@ -197,8 +286,8 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
                     long long ld_out, char* err, size_t errlen) {
     int rc = ensure_wcache(p, err, errlen);
     if (rc) return rc;
-    std::vector<int> u256, u128, m128;
-    build_tiles(p, t0, t1, idw, u256, u128, m128);
+    TileSets ts;
+    build_tiles(p, t0, t1, idw, ts);
     const int total_tiles = (int)(p->c_pad / kCellsPerCta);
     for (int tile0 = 0; tile0 < total_tiles; tile0 += p->w_chunk_tiles) {
         const int n_tiles = std::min(p->w_chunk_tiles, total_tiles - tile0);
@@ -219,38 +308,35 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
         a.n_stages = p->n_stages;
         a.t_lo = t0;
         a.t_hi = t1;
-        if (!u256.empty() && (rc = launch_contract<16, false>(p, a, u256, err, errlen))) return rc;
-        if (!u128.empty() && (rc = launch_contract<8, false>(p, a, u128, err, errlen))) return rc;
-        if (!m128.empty() && (rc = launch_contract<8, true>(p, a, m128, err, errlen))) return rc;
+        if (!ts.u[8].empty() && (rc = launch_contract<8, false>(p, a, ts.u[8], err, errlen))) return rc;
+        if (!ts.u[6].empty() && (rc = launch_contract<6, false>(p, a, ts.u[6], err, errlen))) return rc;
+        if (!ts.u[4].empty() && (rc = launch_contract<4, false>(p, a, ts.u[4], err, errlen))) return rc;
+        if (!ts.u[2].empty() && (rc = launch_contract<2, false>(p, a, ts.u[2], err, errlen))) return rc;
+        if (!ts.m[4].empty() && (rc = launch_contract<4, true>(p, a, ts.m[4], err, errlen))) return rc;
+        if (!ts.m[2].empty() && (rc = launch_contract<2, true>(p, a, ts.m[2], err, errlen))) return rc;
     }
     return IPR_OK;
 }
 
-// Split [t0, t1) into date tiles.  Tiles start on granule boundaries (multiples of 128, absolute);
-// granules containing any NA inside the window take the masked variant (when `use_mask`),
-// adjacent unmasked granules are merged into 256-date tiles.
-void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, std::vector<int>& u256, std::vector<int>& u128,
-                 std::vector<int>& m128) {
-    const int start = t0 - t0 % kGran;
-    std::vector<std::pair<int, bool>> blocks;  // (start, masked)
-    for (int b = start; b < t1; b += 128) {
+// Split [t0, t1) into date tiles on granule boundaries (multiples of 128 dates, absolute).  A
+// granule with any NA inside the window (when `use_mask`) becomes two masked 64-date tiles, the
+// others one 128-date tile; the width actually computed is trimmed to the window in steps of
+// 32 dates (NP = 2, 4, 6, 8), so the ragged last granule does not pay for empty columns.
+void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, TileSets& ts) {
+    for (int b = t0 - t0 % kGran; b < t1; b += kGran) {
+        const int lo = std::max(b, t0), hi = std::min(b + kGran, t1);
         bool na = false;
-        if (use_mask) {
-            const int lo = std::max(b, t0), hi = std::min(b + 128, t1);
+        if (use_mask)
             for (int t = lo; t < hi; t++) na |= (p->h_has_na[t] != 0);
-        }
-        blocks.emplace_back(b, na);
-    }
-    for (size_t i = 0; i < blocks.size();) {
-        if (blocks[i].second) {
-            m128.push_back(blocks[i].first);
-            i++;
-        } else if (i + 1 < blocks.size() && !blocks[i + 1].second) {
-            u256.push_back(blocks[i].first);
-            i += 2;
+        if (na) {
+            for (int h = b; h < b + kGran; h += 64) {
+                if (h >= hi || h + 64 <= lo) continue;
+                const int used = std::min(hi, h + 64) - h;      // columns of this half that are needed
+                ts.m[used > 32 ? 4 : 2].push_back(h);
+            }
         } else {
-            u128.push_back(blocks[i].first);
-            i++;
+            const int used = hi - b;
+            ts.u[used > 96 ? 8 : used > 64 ? 6 : used > 32 ? 4 : 2].push_back(b);
         }
     }
 }
@@ -306,13 +392,13 @@ int scan_zero_pairs(ipr_plan* p, char* err, size_t errlen) {
     }
     off.push_back(n);
     p->n_fix = (int)cell.size();
-    cudaFree(p->d_fix_cell);
-    cudaFree(p->d_fix_off);
-    cudaFree(p->d_fix_st);
+    dev_free(p->d_fix_cell);
+    dev_free(p->d_fix_off);
+    dev_free(p->d_fix_st);
     p->d_fix_cell = p->d_fix_off = p->d_fix_st = nullptr;
-    IPR_CUDA(cudaMalloc(&p->d_fix_cell, sizeof(int) * cell.size()));
-    IPR_CUDA(cudaMalloc(&p->d_fix_off, sizeof(int) * off.size()));
-    IPR_CUDA(cudaMalloc(&p->d_fix_st, sizeof(int) * st.size()));
+    IPR_CUDA(dev_malloc(&p->d_fix_cell, sizeof(int) * cell.size()));
+    IPR_CUDA(dev_malloc(&p->d_fix_off, sizeof(int) * off.size()));
+    IPR_CUDA(dev_malloc(&p->d_fix_st, sizeof(int) * st.size()));
     IPR_CUDA(cudaMemcpy(p->d_fix_cell, cell.data(), sizeof(int) * cell.size(), cudaMemcpyHostToDevice));
     IPR_CUDA(cudaMemcpy(p->d_fix_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
     IPR_CUDA(cudaMemcpy(p->d_fix_st, st.data(), sizeof(int) * st.size(), cudaMemcpyHostToDevice));
@@ -423,18 +509,18 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     PLAN_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     PLAN_CUDA(cudaEventCreate(&p->ev0));
     PLAN_CUDA(cudaEventCreate(&p->ev1));
-    PLAN_CUDA(cudaMalloc(&p->d_cell, sizeof(double2) * p->c_pad));
-    PLAN_CUDA(cudaMalloc(&p->d_st, sizeof(double2) * (p->s_pad + kKT)));
-    PLAN_CUDA(cudaMalloc(&p->d_obs, sizeof(double) * (size_t)n_dates * n_st));
-    PLAN_CUDA(cudaMalloc(&p->d_z0, sizeof(double) * p->z_doubles));
-    PLAN_CUDA(cudaMalloc(&p->d_mask, sizeof(double) * p->z_doubles));
-    PLAN_CUDA(cudaMalloc(&p->d_flag, (size_t)p->n_gran * kGran));
-    PLAN_CUDA(cudaMalloc(&p->d_has_na, (size_t)p->n_gran * kGran));
-    PLAN_CUDA(cudaMalloc(&p->d_counters, sizeof(int) * 4));
-    PLAN_CUDA(cudaMalloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
-    PLAN_CUDA(cudaMalloc(&p->d_wsum, sizeof(double) * p->c_pad));
-    PLAN_CUDA(cudaMalloc(&p->d_perm, sizeof(int) * n_st));
-    PLAN_CUDA(cudaMalloc(&p->d_active_total, sizeof(unsigned long long)));
+    PLAN_CUDA(dev_malloc(&p->d_cell, sizeof(double2) * p->c_pad));
+    PLAN_CUDA(dev_malloc(&p->d_st, sizeof(double2) * (p->s_pad + kKT)));
+    PLAN_CUDA(dev_malloc(&p->d_obs, sizeof(double) * (size_t)n_dates * n_st));
+    PLAN_CUDA(dev_malloc(&p->d_z0, sizeof(double) * p->z_doubles));
+    PLAN_CUDA(dev_malloc(&p->d_mask, sizeof(double) * p->z_doubles));
+    PLAN_CUDA(dev_malloc(&p->d_flag, (size_t)p->n_gran * kGran));
+    PLAN_CUDA(dev_malloc(&p->d_has_na, (size_t)p->n_gran * kGran));
+    PLAN_CUDA(dev_malloc(&p->d_counters, sizeof(int) * 4));
+    PLAN_CUDA(dev_malloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
+    PLAN_CUDA(dev_malloc(&p->d_wsum, sizeof(double) * p->c_pad));
+    PLAN_CUDA(dev_malloc(&p->d_perm, sizeof(int) * n_st));
+    PLAN_CUDA(dev_malloc(&p->d_active_total, sizeof(unsigned long long)));
     PLAN_CUDA(cudaMemsetAsync(p->d_active_total, 0, sizeof(unsigned long long), p->stream));
     PLAN_CUDA(cudaMemsetAsync(p->d_z0, 0, sizeof(double) * p->z_doubles, p->stream));
     PLAN_CUDA(cudaMemsetAsync(p->d_mask, 0, sizeof(double) * p->z_doubles, p->stream));
@@ -483,24 +569,24 @@ void ipr_plan_destroy(ipr_plan* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
-    cudaFree(p->d_cell);
-    cudaFree(p->d_st);
-    cudaFree(p->d_obs);
-    cudaFree(p->d_z0);
-    cudaFree(p->d_mask);
-    cudaFree(p->d_flag);
-    cudaFree(p->d_has_na);
-    cudaFree(p->d_counters);
-    cudaFree(p->d_pairs);
-    cudaFree(p->d_fix_cell);
-    cudaFree(p->d_fix_off);
-    cudaFree(p->d_fix_st);
-    cudaFree(p->d_wfrag);
-    cudaFree(p->d_wsum);
-    cudaFree(p->d_stage_list);
-    cudaFree(p->d_n_active);
-    cudaFree(p->d_perm);
-    cudaFree(p->d_active_total);
+    dev_free(p->d_cell);
+    dev_free(p->d_st);
+    dev_free(p->d_obs);
+    dev_free(p->d_z0);
+    dev_free(p->d_mask);
+    dev_free(p->d_flag);
+    dev_free(p->d_has_na);
+    dev_free(p->d_counters);
+    dev_free(p->d_pairs);
+    dev_free(p->d_fix_cell);
+    dev_free(p->d_fix_off);
+    dev_free(p->d_fix_st);
+    dev_free(p->d_wfrag);
+    dev_free(p->d_wsum);
+    dev_free(p->d_stage_list);
+    dev_free(p->d_n_active);
+    dev_free(p->d_perm);
+    dev_free(p->d_active_total);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -606,6 +692,12 @@ int ipr_plan_stage_blocks(ipr_plan* p, uint64_t* executed, uint64_t* dense) {
     return IPR_OK;
 }
 
+void ipr_release_cached_memory(void) {
+    DevicePool& P = pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.drain_locked();
+}
+
 void ipr_plan_reset_cache(ipr_plan* p) {
     if (p) p->w_mode = -1;
 }
@@ -680,17 +772,20 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
         cudaEvent_t done[kRing] = {nullptr, nullptr, nullptr}, computed[kRing] = {nullptr, nullptr, nullptr};
         cudaStream_t copy = nullptr;
         ~Guard() {
+            Trace td;
             cudaSetDevice(p->device);
             if (copy) {
                 cudaStreamSynchronize(copy);
                 cudaStreamDestroy(copy);
             }
             for (int i = 0; i < kRing; i++) {
-                cudaFree(ring[i]);
+                dev_free(ring[i]);
                 if (done[i]) cudaEventDestroy(done[i]);
                 if (computed[i]) cudaEventDestroy(computed[i]);
             }
+            td.mark("(teardown) ring freed");
             ipr_plan_destroy(p);
+            td.mark("(teardown) plan destroyed");
         }
     } g{plan};
     tr.mark("plan created (allocations, coordinate upload, zero-distance scan)");
@@ -717,7 +812,7 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
     IPR_CUDA(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
     const int n_ring = std::min<int>(kRing, (int)items.size());
     for (int i = 0; i < n_ring; i++) {
-        IPR_CUDA(cudaMalloc(&g.ring[i], sizeof(double) * slot_doubles));
+        IPR_CUDA(dev_malloc(&g.ring[i], sizeof(double) * slot_doubles));
         IPR_CUDA(cudaEventCreateWithFlags(&g.done[i], cudaEventDisableTiming));
         IPR_CUDA(cudaEventCreateWithFlags(&g.computed[i], cudaEventDisableTiming));
     }
@@ -756,6 +851,7 @@ int run_host_job(const HostJob& job, const int* devices, int n_devices, char* er
         set_err(err, errlen, "n_cells, n_st and n_dates must be positive");
         return IPR_EINVAL;
     }
+    Trace tj;
     std::vector<int> devs;
     if (!devices || n_devices <= 0) devs.push_back(0);
     else devs.assign(devices, devices + n_devices);
@@ -791,6 +887,7 @@ int run_host_job(const HostJob& job, const int* devices, int n_devices, char* er
         for (auto& t : th) t.join();
     }
     if (registered) cudaHostUnregister(job.out);
+    tj.mark("(job) all device blocks done");
     for (int g = 0; g < G; g++)
         if (rcs[g] != IPR_OK) {
             set_err(err, errlen, "device %d: %s", devs[g], errs[g].c_str());

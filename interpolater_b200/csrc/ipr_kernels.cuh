@@ -14,8 +14,11 @@
 //                    ~10 FP64-pipe instructions per weight per 256 dates — the FP64 pipe is the
 //                    roofline here, HBM is idle — so the weights are traded to HBM: +0.3 % time for
 //                    the generation pass, -7 % in the contraction.)
-//   contract_kernel  C tile = 64 cells x (128|256) dates per CTA, 8 warps x (8 cells x all dates),
-//                    accumulators in registers (128/thread).  A fragments: one coalesced LDG.64 per
+//   contract_kernel  C tile = 64 cells x 128 dates per CTA (64 dates x {numerator, mask} when the
+//                    granule holds NA), 8 warps x (8 cells x all dates), 64 accumulator registers
+//                    per thread -> 128 registers, TWO CTAs per SM: one CTA's prologue / epilogue /
+//                    barrier waits hide under the other's DMMAs (measured 92.5 % -> 95.5 % of peak
+//                    against one 256-date CTA per SM).  A fragments: one coalesced LDG.64 per
 //                    lane per k-step, prefetched a stage ahead.  B (z0 / mask granule blocks, see
 //                    below): L2 -> shared memory with cp.async.bulk (TMA bulk engine, UBLKCP) through
 //                    a kStages-deep mbarrier pipeline; a slot is refilled by the last warp that
@@ -33,14 +36,10 @@ constexpr int kConsumerWarps = 8;
 constexpr int kThreads = kConsumerWarps * 32;
 constexpr int kCellsPerCta = kConsumerWarps * 8;     // 64
 #ifndef IPR_KT
-#define IPR_KT 32
-#endif
-#ifndef IPR_STAGES
-#define IPR_STAGES 3
+#define IPR_KT 16
 #endif
 constexpr int kKT = IPR_KT;                          // stations per pipeline stage
 constexpr int kKSteps = kKT / 4;                     // DMMA k-steps per stage
-constexpr int kStages = IPR_STAGES;
 constexpr int kMaxTilesPerLaunch = 56;
 // Device layout of the B operand ("granule blocks"): dates are cut into granules of 128, stations
 // into pipeline stages of kKT; block (g, stage) = [kKT rows][kGranLd doubles] is ONE contiguous
@@ -69,7 +68,7 @@ struct WeightParams {
 
 struct TileList {
     int n;
-    int t0[kMaxTilesPerLaunch];   // absolute start date of each tile (multiple of 16)
+    int t0[kMaxTilesPerLaunch];   // absolute start date of each tile (multiple of 128; of 64 when masked)
 };
 
 struct ContractArgs {
@@ -185,11 +184,10 @@ __device__ __forceinline__ double weight_from_d2(double d2, const WeightParams& 
     }
 }
 
-template <int NP, bool MASKED>
+template <bool MASKED>
 struct SmemLayout {
-    static_assert(NP == 8 || (NP == 16 && !MASKED), "tile = 1 or 2 granules of z0, or z0 + mask granule");
-    static constexpr int kW = 16 * NP;                            // dates per tile
-    static constexpr int kBlocks = (NP == 16 || MASKED) ? 2 : 1;  // granule blocks per stage
+    static constexpr int kBlocks = MASKED ? 2 : 1;   // granule blocks per stage (z0 [+ mask])
+    static constexpr int kStages = MASKED ? 3 : 5;   // pipeline depth (two CTAs share the SM's 227 KB)
     static constexpr int kStageBytes = kBlocks * kBlkBytes;
     static constexpr int kBarOff = kStageBytes * kStages;
     static constexpr int kTotal = kBarOff + kStages * 8 + kStages * 4 + 16;
@@ -197,11 +195,12 @@ struct SmemLayout {
 };
 
 // Refill one pipeline stage: one bulk copy (TMA bulk engine) per granule block.  Called by one lane.
-template <int NP, bool MASKED>
+// it = position in the tile's active-stage list (selects the slot), sid = the stage itself.
+template <bool MASKED>
 __device__ __forceinline__ void produce_stage(const ContractArgs& args, unsigned char* smem, uint64_t* full_bar,
                                               int it, int sid, int gran0) {
-    using L = SmemLayout<NP, MASKED>;
-    const int slot = it % kStages;  // it: position in the tile's active-stage list; sid: the stage
+    using L = SmemLayout<MASKED>;
+    const int slot = it % L::kStages;
     unsigned char* stage = smem + slot * L::kStageBytes;
     // generic-proxy reads of this slot (all warps, ordered by the release counter) precede the
     // async-proxy writes issued below
@@ -209,11 +208,7 @@ __device__ __forceinline__ void produce_stage(const ContractArgs& args, unsigned
     mbar_expect_tx(&full_bar[slot], L::kTxBytes);
     const size_t b0 = ((size_t)gran0 * args.n_stages + sid) * kBlkDoubles;
     bulk_g2s(stage, args.z0 + b0, kBlkBytes, &full_bar[slot]);
-    if (MASKED) {
-        bulk_g2s(stage + kBlkBytes, args.mask + b0, kBlkBytes, &full_bar[slot]);
-    } else if (NP == 16) {
-        bulk_g2s(stage + kBlkBytes, args.z0 + b0 + (size_t)args.n_stages * kBlkDoubles, kBlkBytes, &full_bar[slot]);
-    }
+    if (MASKED) bulk_g2s(stage + kBlkBytes, args.mask + b0, kBlkBytes, &full_bar[slot]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -276,25 +271,30 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
 
 // ---------------------------------------------------------------------------------------------
 // DMMA contraction + normalise epilogue
-//   NP     : number of 16-date column groups per tile (tile width 16*NP dates)
-//   MASKED : also contract the availability mask (IDW with NA in the tile: 4*S flop/cell-day)
+//   NP     : number of 16-date column groups computed (tile width 16*NP dates: 128 for a full
+//            unmasked granule, 64 for a masked half granule, less for the ragged last granule)
+//   MASKED : also contract the availability mask (IDW with NA in the granule: 4*S flop/cell-day)
 // grid.x = n_cell_tiles * n_tiles, date tile fastest: CTAs that run together share the A tile
 // through L2 and the whole B operand (tens of MB) stays L2-resident.
 // ---------------------------------------------------------------------------------------------
 template <int NP, bool MASKED>
-__global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArgs args) {
-    using L = SmemLayout<NP, MASKED>;
+__global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArgs args) {
+    using L = SmemLayout<MASKED>;
+    constexpr int kStages = L::kStages;
+    static_assert(NP >= 1 && NP <= (MASKED ? 4 : 8), "64 accumulator registers per thread");
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-    // release counters: a slot is refilled by whichever warp is the LAST to finish reading it
+    // release counters: a slot is refilled by whichever warp is the LAST to finish reading it, so
+    // no warp ever blocks on "slot empty"
     int* release_cnt = reinterpret_cast<int*>(full_bar + kStages);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tile_idx = blockIdx.x % args.tiles.n;
     const int ct_local = blockIdx.x / args.tiles.n;
-    const int tile_t0 = args.tiles.t0[tile_idx];   // multiple of kGran
+    const int tile_t0 = args.tiles.t0[tile_idx];
     const int gran0 = tile_t0 / kGran;
+    const int col0 = tile_t0 % kGran;   // 0, or 64 for the second masked half of a granule
     // the tile's list of stages with any non-zero weight (all of them for IDW; for Cressman only
     // the stations near the tile: the rest of the dense product is exactly zero and is skipped)
     const int* list = args.stage_list + (size_t)ct_local * args.n_stages;
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int it = 0; it < kStages && it < n_stages; it++)
-            produce_stage<NP, MASKED>(args, smem, full_bar, it, __ldg(list + it), gran0);
+            produce_stage<MASKED>(args, smem, full_bar, it, __ldg(list + it), gran0);
     }
 
     const int q = lane & 3;   // k index inside a k-step (A column / B row)
@@ -355,12 +355,12 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
 #pragma unroll
         for (int kk = 0; kk < kKSteps; kk++) {
             const double a = w_cur[kk];
-            const double* zrow = zs + (kk * 4 + q) * kGranLd + 2 * r;
+            const double* zrow = zs + (kk * 4 + q) * kGranLd + col0 + 2 * r;
             const double* mrow = zrow + kBlkDoubles;  // mask granule block follows the z0 block
 #pragma unroll
             for (int i = 0; i < NP; i++) {
-                // column group i lives in granule block i/8 (256-date tiles span two blocks)
-                const double2 b = *reinterpret_cast<const double2*>(zrow + (i >> 3) * kBlkDoubles + 16 * (i & 7));
+                // one LDS.128 = the thread's B elements of two adjacent column groups -> two DMMAs
+                const double2 b = *reinterpret_cast<const double2*>(zrow + 16 * i);
                 dmma884(acc[2 * i][0], acc[2 * i][1], a, b.x);
                 dmma884(acc[2 * i + 1][0], acc[2 * i + 1][1], a, b.y);
                 if (MASKED) {
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const ContractArg
                 release_cnt[slot] = 0;
                 __threadfence_block();
                 if (it + kStages < n_stages)
-                    produce_stage<NP, MASKED>(args, smem, full_bar, it + kStages, __ldg(list + it + kStages), gran0);
+                    produce_stage<MASKED>(args, smem, full_bar, it + kStages, __ldg(list + it + kStages), gran0);
             }
         }
 #pragma unroll
