@@ -341,7 +341,7 @@ def run_ours(a):
         "unit": "TFLOP/s",
         "frac": achieved / peaks["dmma_tflops"],
         "traffic": None,
-        "kernel": "ipr::contract_kernel<16,false> (FP64 DMMA.8x8x4)",
+        "kernel": "ipr::contract_kernel<8,%s> (FP64 DMMA.8x8x4, 2 CTAs/SM)" % ("true" if a.workload == "idw_masked" else "false"),
         "peak_source": "profiles/fp64_peaks.json: DMMA m8n8k4 probe measured on this pool's B200 "
                        "(MEASURED_PEAKS.json has no FP64 entry); cuBLAS DGEMM 8192^3 = %.1f TFLOP/s"
                        % peaks["cublas_dgemm_tflops_burst"],
