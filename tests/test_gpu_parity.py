@@ -110,6 +110,67 @@ def test_cressman_radius_without_neighbours_is_all_na():
     assert np.isnan(got).all()
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_shapes_against_oracle(seed):
+    """Ragged sizes around every tiling boundary (64-cell tiles, 16-station stages, 64/128-date
+    tiles), random NA density, co-located stations, random power / radii."""
+    rng = np.random.default_rng(1000 + seed)
+    ncol, nrow = int(rng.integers(1, 24)), int(rng.integers(1, 14))
+    n_st = int(rng.choice([1, 2, 15, 16, 17, 31, 33, 48, 70]))
+    n_dates = int(rng.choice([1, 2, 31, 32, 33, 63, 64, 65, 96, 127, 128, 129, 191, 193, 257, 300]))
+    na_frac = float(rng.choice([0.0, 0.0, 0.03, 0.5]))
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(ncol, nrow, n_st, n_dates, na_frac=na_frac,
+                                                   plant_zero_dist=int(min(n_st, ncol * nrow, rng.integers(0, 3))),
+                                                   seed=5000 + seed)
+    if n_dates > 40 and na_frac == 0.0 and seed % 2:
+        obs[int(rng.integers(0, n_dates)), int(rng.integers(0, n_st))] = np.nan   # a single NA -> one masked granule
+    p = float(rng.choice([1.0, 2.0, 2.0, 2.5, 4.0]))
+    assert_parity(engine.idw_grid(cx, cy, sx, sy, obs, p=p), ref.idw_reference(cx, cy, sx, sy, obs, p),
+                  label=f"idw seed={seed} {ncol}x{nrow} S={n_st} D={n_dates} na={na_frac} p={p}")
+    radii = ref.cressman_radii_m(rng.choice([0.7, 1.5, 3, 6, 12, 40], size=int(rng.integers(1, 4)), replace=False))
+    got = engine.cressman_grid(cx, cy, sx, sy, obs, radii)
+    want = ref.cressman_reference(cx, cy, sx, sy, obs, radii)
+    for i in range(len(radii)):
+        assert_parity(got[i], want[i], label=f"cressman seed={seed} R={radii[i]}")
+
+
+def test_many_stations_and_wide_station_extent():
+    """More stations than one shared-memory chunk of the weight kernel (1024) and stations far
+    outside the grid (Morton order must cope with a bounding box much larger than the raster)."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(9, 7, 1100, 5, na_frac=0.1, seed=31)
+    sx[::7] += 3.0e6
+    sy[::11] -= 2.0e6
+    assert_parity(engine.idw_grid(cx, cy, sx, sy, obs), ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="S=1100")
+    radii = np.array([2000.0, 9000.0])
+    got = engine.cressman_grid(cx, cy, sx, sy, obs, radii)
+    want = ref.cressman_reference(cx, cy, sx, sy, obs, radii)
+    for i in range(2):
+        assert_parity(got[i], want[i], label=f"S=1100 cressman {i}")
+
+
+def test_duplicate_cells_and_all_stations_on_cells():
+    """Every station sits on a cell centre and some cells are listed twice (the C ABI takes arbitrary
+    cell arrays): zero-distance bookkeeping with many pairs."""
+    cx, cy = synthetic.regular_grid(6, 5)
+    cx = np.concatenate([cx, cx[:7]])
+    cy = np.concatenate([cy, cy[:7]])
+    rng = np.random.default_rng(8)
+    idx = rng.choice(30, 12, replace=False)
+    sx, sy = cx[idx].copy(), cy[idx].copy()
+    obs = np.round(rng.gamma(0.8, 8.0, (9, 12)), 1)
+    obs[rng.random(obs.shape) < 0.25] = np.nan
+    assert_parity(engine.idw_grid(cx, cy, sx, sy, obs), ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="dups")
+
+
+def test_buffer_pool_release():
+    lib = _native.load()
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(300, 300, 64, 130)
+    a = engine.idw_grid(cx, cy, sx, sy, obs)
+    lib.ipr_release_cached_memory()
+    b = engine.idw_grid(cx, cy, sx, sy, obs)
+    assert np.array_equal(a, b, equal_nan=True)
+
+
 # ---------------------------------------------------------------- golden fixtures
 def test_synthetic_golden(synthetic_golden):
     g = synthetic_golden
