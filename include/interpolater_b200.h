@@ -50,7 +50,9 @@ double ipr_na_real(void);
  *                    columns of BD_Obs are); NaN/NA = missing
  *   devices          n_devices CUDA ordinals (NULL / 0 => device 0); date blocks are sharded
  *                    contiguously over them, no inter-GPU reduction
- *   out              caller-owned, column-major n_cells x n_dates (one layer per date)
+ *   out              caller-owned, column-major n_cells x n_dates (one layer per date); page-locked
+ *                    memory receives the D2H copies directly, pageable memory (an R vector) is
+ *                    filled through a pinned staging ring with a multi-threaded first touch
  * ------------------------------------------------------------------------------------- */
 int ipr_idw_f64(const double* cell_x, const double* cell_y, int64_t n_cells,
                 const double* st_x, const double* st_y, int32_t n_st,

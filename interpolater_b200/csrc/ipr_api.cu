@@ -4,6 +4,7 @@
 #include "../../include/interpolater_b200.h"
 
 #include <algorithm>
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <chrono>
@@ -742,9 +743,145 @@ struct HostJob {
     const double* radii;
     int n_radii;
     double* out;
+    bool out_pinned = false;  // caller's output is page-locked: D2H lands in it directly
 };
 
 constexpr int kRing = 3;
+
+// ---------------------------------------------------------------------------------------------
+// Pageable destination (what R allocates): D2H goes through a small ring of pinned staging slots
+// and a drain thread fans every slot out to the caller's memory with parallel memcpy.  Pinning a
+// fresh 29 GB matrix with cudaHostRegister instead was measured at 7.2 s (page faults taken one by
+// one inside the driver); first-touching it from many threads is what makes this path fast.
+// ---------------------------------------------------------------------------------------------
+class PageableSink {
+public:
+    static constexpr size_t kSlotBytes = 256u << 20;
+    static constexpr int kSlots = 4;
+
+    ~PageableSink() { finish(); }
+
+    int start() {
+        for (int i = 0; i < kSlots; i++) {
+            {   // pinned slots are recycled process-wide (cudaHostAlloc is slow), one set per sink
+                std::lock_guard<std::mutex> lk(pinned_mu());
+                if (!pinned_free().empty()) {
+                    slot_[i] = pinned_free().back();
+                    pinned_free().pop_back();
+                }
+            }
+            if (!slot_[i] && cudaHostAlloc(&slot_[i], kSlotBytes, cudaHostAllocPortable) != cudaSuccess) {
+                slot_[i] = nullptr;
+                cudaGetLastError();
+                return IPR_ENOMEM;
+            }
+            if (cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
+                return IPR_ECUDA;
+        }
+        n_threads_ = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        drain_ = std::thread([this] { drain_loop(); });
+        started_ = true;
+        return IPR_OK;
+    }
+
+    // enqueue device -> host copy of `bytes` from d_src to pageable dst, on `stream`
+    int push(const char* d_src, char* dst, size_t bytes, cudaStream_t stream) {
+        for (size_t off = 0; off < bytes; off += kSlotBytes) {
+            const size_t n = std::min(kSlotBytes, bytes - off);
+            const long long id = issued_;
+            const int k = (int)(id % kSlots);
+            {   // wait until the slot's previous contents have been drained
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return drained_ >= id - kSlots + 1 || failed_; });
+                if (failed_) return IPR_ECUDA;
+            }
+            if (cudaMemcpyAsync(slot_[k], d_src + off, n, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                cudaEventRecord(ev_[k], stream) != cudaSuccess)
+                return IPR_ECUDA;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                work_.push_back({dst + off, n});
+                issued_++;
+            }
+            cv_.notify_all();
+        }
+        return IPR_OK;
+    }
+
+    int finish() {
+        if (!started_) {
+            release_slots();
+            return IPR_OK;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            done_ = true;
+        }
+        cv_.notify_all();
+        if (drain_.joinable()) drain_.join();
+        for (int i = 0; i < kSlots; i++)
+            if (ev_[i]) cudaEventDestroy(ev_[i]);
+        release_slots();
+        started_ = false;
+        return failed_ ? IPR_ECUDA : IPR_OK;
+    }
+
+private:
+    struct Work { char* dst; size_t bytes; };
+    static std::mutex& pinned_mu() { static std::mutex m; return m; }
+    static std::vector<void*>& pinned_free() { static std::vector<void*> v; return v; }
+    void release_slots() {
+        std::lock_guard<std::mutex> lk(pinned_mu());
+        for (int i = 0; i < kSlots; i++)
+            if (slot_[i]) {
+                pinned_free().push_back(slot_[i]);
+                slot_[i] = nullptr;
+            }
+    }
+
+    void drain_loop() {
+        for (long long id = 0;; id++) {
+            Work w;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return issued_ > id || done_; });
+                if (issued_ <= id) return;
+                w = work_[id];
+            }
+            const int k = (int)(id % kSlots);
+            if (cudaEventSynchronize(ev_[k]) != cudaSuccess) {
+                std::lock_guard<std::mutex> lk(mu_);
+                failed_ = true;
+                cv_.notify_all();
+                return;
+            }
+            // parallel first-touch + copy
+            const char* src = static_cast<const char*>(slot_[k]);
+            const size_t per = (w.bytes / n_threads_ + 4095) & ~size_t(4095);
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < n_threads_; t++) {
+                const size_t lo = std::min(w.bytes, (size_t)t * per), hi = std::min(w.bytes, lo + per);
+                if (hi > lo) th.emplace_back([=] { memcpy(w.dst + lo, src + lo, hi - lo); });
+            }
+            for (auto& x : th) x.join();
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                drained_ = id + 1;
+            }
+            cv_.notify_all();
+        }
+    }
+
+    void* slot_[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    std::thread drain_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<Work> work_;
+    long long issued_ = 0, drained_ = 0;
+    bool done_ = false, failed_ = false, started_ = false;
+    unsigned n_threads_ = 1;
+};
 
 // IPR_TRACE=1: phase timestamps of the host-buffer path on stderr
 struct Trace {
@@ -810,6 +947,11 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
     }
     const size_t slot_doubles = (size_t)job.n_cells * std::min(chunk, (int)round_up(nd, 16));
     IPR_CUDA(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+    PageableSink sink;
+    if (!job.out_pinned && (rc = sink.start())) {
+        set_err(err, errlen, "could not set up the pinned staging ring for a pageable output buffer");
+        return rc;
+    }
     const int n_ring = std::min<int>(kRing, (int)items.size());
     for (int i = 0; i < n_ring; i++) {
         IPR_CUDA(dev_malloc(&g.ring[i], sizeof(double) * slot_doubles));
@@ -830,8 +972,14 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
         IPR_CUDA(cudaEventRecord(g.computed[slot], plan->stream));
         IPR_CUDA(cudaStreamWaitEvent(g.copy, g.computed[slot], 0));
         double* dst = job.out + (size_t)it.stack * job.n_cells * job.n_dates + (size_t)(d0 + it.t0) * job.n_cells;
-        IPR_CUDA(cudaMemcpyAsync(dst, g.ring[slot], sizeof(double) * (size_t)job.n_cells * (it.t1 - it.t0),
-                                 cudaMemcpyDeviceToHost, g.copy));
+        const size_t bytes = sizeof(double) * (size_t)job.n_cells * (it.t1 - it.t0);
+        if (job.out_pinned) {
+            IPR_CUDA(cudaMemcpyAsync(dst, g.ring[slot], bytes, cudaMemcpyDeviceToHost, g.copy));
+        } else if ((rc = sink.push(reinterpret_cast<const char*>(g.ring[slot]), reinterpret_cast<char*>(dst), bytes,
+                                   g.copy))) {
+            set_err(err, errlen, "staged device-to-host copy failed");
+            return rc;
+        }
         IPR_CUDA(cudaEventRecord(g.done[slot], g.copy));
     }
     tr.mark("all chunks submitted");
@@ -839,6 +987,11 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
     tr.mark("compute stream drained");
     IPR_CUDA(cudaStreamSynchronize(g.copy));
     tr.mark("copy stream drained");
+    if ((rc = sink.finish())) {
+        set_err(err, errlen, "staged device-to-host copy failed");
+        return rc;
+    }
+    tr.mark("host staging drained");
     return IPR_OK;
 }
 
@@ -856,18 +1009,13 @@ int run_host_job(const HostJob& job, const int* devices, int n_devices, char* er
     if (!devices || n_devices <= 0) devs.push_back(0);
     else devs.assign(devices, devices + n_devices);
     const int G = (int)devs.size();
-    // pin the caller's output for asynchronous D2H unless it already is pinned; failure to pin is
-    // not an error (the copies then go through the driver's pageable path)
-    const size_t out_bytes = sizeof(double) * (size_t)job.n_cells * job.n_dates * (job.cressman ? job.n_radii : 1);
-    bool registered = false;
+    // is the caller's output page-locked (then D2H lands in it directly), or pageable (staged)?
+    HostJob jobx = job;
     {
         cudaPointerAttributes attr;
         cudaError_t e = cudaPointerGetAttributes(&attr, job.out);
         if (e != cudaSuccess) cudaGetLastError();
-        if (e != cudaSuccess || attr.type == cudaMemoryTypeUnregistered) {
-            if (cudaHostRegister(job.out, out_bytes, cudaHostRegisterPortable) == cudaSuccess) registered = true;
-            else cudaGetLastError();
-        }
+        jobx.out_pinned = (e == cudaSuccess && attr.type == cudaMemoryTypeHost);
     }
     // date blocks: multiples of 128 dates so that tiles stay aligned; remainder to the last devices
     std::vector<int> bounds(G + 1, 0);
@@ -879,14 +1027,13 @@ int run_host_job(const HostJob& job, const int* devices, int n_devices, char* er
     std::vector<int> rcs(G, IPR_OK);
     std::vector<std::string> errs(G, std::string(256, '\0'));
     if (G == 1) {
-        rcs[0] = run_device_block(job, devs[0], bounds[0], bounds[1], &errs[0][0], errs[0].size());
+        rcs[0] = run_device_block(jobx, devs[0], bounds[0], bounds[1], &errs[0][0], errs[0].size());
     } else {
         std::vector<std::thread> th;
         for (int g = 0; g < G; g++)
-            th.emplace_back([&, g] { rcs[g] = run_device_block(job, devs[g], bounds[g], bounds[g + 1], &errs[g][0], errs[g].size()); });
+            th.emplace_back([&, g] { rcs[g] = run_device_block(jobx, devs[g], bounds[g], bounds[g + 1], &errs[g][0], errs[g].size()); });
         for (auto& t : th) t.join();
     }
-    if (registered) cudaHostUnregister(job.out);
     tj.mark("(job) all device blocks done");
     for (int g = 0; g < G; g++)
         if (rcs[g] != IPR_OK) {
