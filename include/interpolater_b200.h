@@ -71,6 +71,30 @@ int ipr_cressman_f64(const double* cell_x, const double* cell_y, int64_t n_cells
                      double* out, char* err, size_t errlen);
 
 /* ---------------------------------------------------------------------------------------
+ * The same two calls with the reference's next steps fused on the device, so that a large stack
+ * needs no further host pass:
+ *   round_mode 0 none | 1 R's round(v, n_round) as in terra::app(x, function(v) round(v, n)),
+ *              R/IDW.R:356-358 | 2 terra's round(SpatRaster, n), R/Cressman.R:353-355
+ *   cell_keep  NULL, or n_cells bytes: cells with 0 are written as NA (terra::mask by the study
+ *              area, R/IDW.R:376-381 — the caller rasterises the polygon)
+ * The reference validates on the rounded, UN-masked stack (R/IDW.R:364-372): a caller that masks
+ * here evaluates the few test-station cells with a separate (tiny) call.
+ * ------------------------------------------------------------------------------------- */
+int ipr_idw_post_f64(const double* cell_x, const double* cell_y, int64_t n_cells,
+                     const double* st_x, const double* st_y, int32_t n_st,
+                     const double* obs, int32_t n_dates, double p,
+                     int32_t round_mode, int32_t n_round, const uint8_t* cell_keep,
+                     const int* devices, int n_devices,
+                     double* out, char* err, size_t errlen);
+int ipr_cressman_post_f64(const double* cell_x, const double* cell_y, int64_t n_cells,
+                          const double* st_x, const double* st_y, int32_t n_st,
+                          const double* obs, int32_t n_dates,
+                          const double* radii_m, int32_t n_radii,
+                          int32_t round_mode, int32_t n_round, const uint8_t* cell_keep,
+                          const int* devices, int n_devices,
+                          double* out, char* err, size_t errlen);
+
+/* ---------------------------------------------------------------------------------------
  * Device-resident plan API (used by the one-shot calls, the benchmark and the Python host
  * mirror): inputs stay in HBM, outputs are written to caller-supplied DEVICE pointers.
  * A plan is bound to one device and owns one compute stream.
@@ -103,6 +127,11 @@ int ipr_plan_cressman(ipr_plan* plan, const double* radii_m, int32_t n_radii,
  * geometry of a plan never changes), so that the next call regenerates it.  The benchmark calls
  * this every step so that a timed step contains the whole hot path. */
 void ipr_plan_reset_cache(ipr_plan* plan);
+
+/* post-pass applied by later ipr_plan_idw / ipr_plan_cressman calls (see ipr_idw_post_f64);
+ * cell_keep is a HOST pointer (copied), NULL clears the mask */
+int ipr_plan_set_post(ipr_plan* plan, int32_t round_mode, int32_t n_round, const uint8_t* cell_keep,
+                      char* err, size_t errlen);
 
 int ipr_plan_sync(ipr_plan* plan);
 /* CUDA events on the plan's stream, for timing exactly what the plan launched */

@@ -18,7 +18,7 @@ ERRLEN = 512
 #: every symbol include/interpolater_b200.h declares (checked by the CPU test-suite)
 EXPORTED_SYMBOLS = [
     "ipr_version", "ipr_device_count", "ipr_na_real",
-    "ipr_idw_f64", "ipr_cressman_f64",
+    "ipr_idw_f64", "ipr_cressman_f64", "ipr_idw_post_f64", "ipr_cressman_post_f64", "ipr_plan_set_post",
     "ipr_plan_create", "ipr_plan_destroy", "ipr_plan_set_obs", "ipr_plan_set_obs_device",
     "ipr_plan_idw", "ipr_plan_cressman", "ipr_plan_sync", "ipr_plan_reset_cache",
     "ipr_plan_timer_start", "ipr_plan_timer_stop", "ipr_plan_launch_count", "ipr_plan_zero_pairs",
@@ -62,6 +62,14 @@ def load() -> C.CDLL:
     lib.ipr_cressman_f64.restype = C.c_int
     lib.ipr_cressman_f64.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, vp, C.c_int32,
                                      ip, C.c_int, vp, C.c_char_p, C.c_size_t]
+    lib.ipr_idw_post_f64.restype = C.c_int
+    lib.ipr_idw_post_f64.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, C.c_double,
+                                     C.c_int32, C.c_int32, vp, ip, C.c_int, vp, C.c_char_p, C.c_size_t]
+    lib.ipr_cressman_post_f64.restype = C.c_int
+    lib.ipr_cressman_post_f64.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, vp, C.c_int32,
+                                          C.c_int32, C.c_int32, vp, ip, C.c_int, vp, C.c_char_p, C.c_size_t]
+    lib.ipr_plan_set_post.restype = C.c_int
+    lib.ipr_plan_set_post.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_char_p, C.c_size_t]
     lib.ipr_plan_create.restype = C.c_int
     lib.ipr_plan_create.argtypes = [C.POINTER(vp), C.c_int, vp, vp, C.c_int64, vp, vp, C.c_int32, C.c_int32,
                                     C.c_char_p, C.c_size_t]

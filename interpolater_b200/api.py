@@ -17,7 +17,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .spatial import GridGeometry, SpatRaster, SpatVector, r_round, terra_round
+from .spatial import GridGeometry, SpatRaster, SpatVector
 from .validation import message, select_data, validate
 
 
@@ -111,18 +111,33 @@ def IDW(BD_Obs, BD_Coord, shapefile, grid_resolution, p=2, Mask=True, n_round=No
     obs = train_data[cols].to_numpy(dtype=np.float64)[rows, :]
 
     # ---- IDW algorithm: the accelerated core (replaces R/IDW.R:249-355) ----
+    # Every cell is independent, so the steps that follow the hot loop in the reference are folded
+    # into the engine calls instead of being host passes over the whole stack:
+    #   * validation (R/IDW.R:364-372, on the rounded UN-masked stack) needs only the cells that
+    #     contain the test stations -> one tiny engine call on those cells;
+    #   * rounding (R/IDW.R:356-358) and crop + mask (R/IDW.R:376-381) -> the main call computes just
+    #     the cropped window, rounds and masks on the device.
     message("Analysis in progress. Please wait...")
-    values = engine.idw_grid(cell_x, cell_y, sx, sy, obs, p=float(p), devices=devices)
-    if n_round is not None:
-        values = np.asfortranarray(r_round(values, n_round))        # R/IDW.R:356-358
-    Ensamble = SpatRaster(geom, values, labels)                       # R/IDW.R:355, :359
-
-    # ---- validation (R/IDW.R:364-372) — on the rounded, un-masked stack ----
+    nr = None if n_round is None else int(n_round)
     if validating:
-        final_results = validate(data_val["test_cords"], data_val["test_data"], Ensamble, Rain_threshold)
-    # ---- mask (R/IDW.R:376-381) ----
+        tc = data_val["test_cords"]
+        cells = geom.cell_from_xy(tc["X"].to_numpy(dtype=np.float64), tc["Y"].to_numpy(dtype=np.float64))
+        sim_pts = np.full((len(cells), len(labels)), np.nan)
+        inside = cells >= 0
+        if inside.any():
+            sim_pts[inside] = engine.idw_grid(cell_x[cells[inside]], cell_y[cells[inside]], sx, sy, obs, p=float(p),
+                                              devices=devices, n_round=nr, round_mode=engine.ROUND_R)
+        final_results = validate(tc, data_val["test_data"], None, Rain_threshold, sim_pts=sim_pts, layer_names=labels)
     if Mask is True:
-        Ensamble = Ensamble.crop_mask(shapefile)
+        sub, sub_cells = geom.crop_window(shapefile)
+        keep = sub.polygon_cover(shapefile)
+        values = engine.idw_grid(cell_x[sub_cells], cell_y[sub_cells], sx, sy, obs, p=float(p), devices=devices,
+                                 n_round=nr, round_mode=engine.ROUND_R, cell_keep=keep)
+        Ensamble = SpatRaster(sub, values, labels)
+    else:
+        values = engine.idw_grid(cell_x, cell_y, sx, sy, obs, p=float(p), devices=devices, n_round=nr,
+                                 round_mode=engine.ROUND_R)
+        Ensamble = SpatRaster(geom, values, labels)                   # R/IDW.R:355, :359
     # ---- save (R/IDW.R:385-395) ----
     if save_model is True:
         if name_save is None:
@@ -183,18 +198,23 @@ def Cressman(BD_Obs, BD_Coord, shapefile, grid_resolution, search_radius, traini
 
     # ---- Cressman core (replaces R/Cressman.R:268-345) ----
     message("Analysis in progress. Please wait...")
-    stacks = engine.cressman_grid(cell_x, cell_y, sx, sy, obs, radii_m, devices=devices)
+    nr = None if n_round is None else int(n_round)
     names = ["%g km" % (r / 1000.0) for r in radii_m]                  # :357
-    Ensamble = {}
-    for i, nm in enumerate(names):
-        vals = np.asfortranarray(stacks[i])
-        if n_round is not None:
-            vals = np.asfortranarray(terra_round(vals, n_round))      # :353-355
-        Ensamble[nm] = SpatRaster(geom, vals, labels)
+    if validating:                                                     # :361-372, on the test-station cells only
+        tc = data_val["test_cords"]
+        cells = geom.cell_from_xy(tc["X"].to_numpy(dtype=np.float64), tc["Y"].to_numpy(dtype=np.float64))
+        inside = cells >= 0
+        sims = np.full((len(radii_m), len(cells), len(labels)), np.nan)
+        if inside.any():
+            sims[:, inside, :] = engine.cressman_grid(cell_x[cells[inside]], cell_y[cells[inside]], sx, sy, obs,
+                                                      radii_m, devices=devices, n_round=nr,
+                                                      round_mode=engine.ROUND_TERRA)
+        final_results = {nm: validate(tc, data_val["test_data"], None, Rain_threshold, sim_pts=sims[i],
+                                      layer_names=labels) for i, nm in enumerate(names)}
+    stacks = engine.cressman_grid(cell_x, cell_y, sx, sy, obs, radii_m, devices=devices, n_round=nr,
+                                  round_mode=engine.ROUND_TERRA)      # rounding :353-355 on the device
+    Ensamble = {nm: SpatRaster(geom, stacks[i], labels) for i, nm in enumerate(names)}
 
-    if validating:                                                     # :361-372
-        final_results = {nm: validate(data_val["test_cords"], data_val["test_data"], Ensamble[nm], Rain_threshold)
-                         for nm in names}
     if save_model is True:                                             # :377-387
         message("Model saved successfully")
         for nm in names:

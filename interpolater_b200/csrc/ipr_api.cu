@@ -184,6 +184,10 @@ struct ipr_plan {
     std::vector<uint8_t> h_has_na;
     bool obs_ready = false;
     long long launches = 0;
+    // optional post-pass (rounding, polygon mask) applied to every finished layer
+    int post_round_mode = 0;
+    double post_p10 = 1.0;
+    uint8_t* d_cell_keep = nullptr;
     // A-operand cache (weights in DMMA fragment order) for a chunk of cell tiles + per-cell sums
     double* d_wfrag = nullptr;
     double* d_wsum = nullptr;
@@ -340,6 +344,16 @@ void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, TileSets& ts)
             ts.u[used > 96 ? 8 : used > 64 ? 6 : used > 32 ? 4 : 2].push_back(b);
         }
     }
+}
+
+int run_post(ipr_plan* p, int t0, int t1, double* d_out, long long ld_out, char* err, size_t errlen) {
+    if (p->post_round_mode == 0 && !p->d_cell_keep) return IPR_OK;
+    dim3 grid((unsigned)((p->n_cells + 255) / 256), (unsigned)std::min(t1 - t0, 64));
+    post_kernel<<<grid, 256, 0, p->stream>>>(d_out, ld_out, p->n_cells, t1 - t0, p->post_round_mode, p->post_p10,
+                                             p->d_cell_keep);
+    IPR_CUDA(cudaGetLastError());
+    p->launches++;
+    return IPR_OK;
 }
 
 int check_range(const ipr_plan* p, int t0, int t1, const double* d_out, long long ld_out, char* err, size_t errlen) {
@@ -587,6 +601,7 @@ void ipr_plan_destroy(ipr_plan* p) {
     dev_free(p->d_stage_list);
     dev_free(p->d_n_active);
     dev_free(p->d_perm);
+    dev_free(p->d_cell_keep);
     dev_free(p->d_active_total);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -652,6 +667,30 @@ int ipr_plan_idw(ipr_plan* p, double pw, int32_t t0, int32_t t1, double* d_out, 
         IPR_CUDA(cudaGetLastError());
         p->launches++;
     }
+    return run_post(p, t0, t1, d_out, ld_out, err, errlen);
+}
+
+int ipr_plan_set_post(ipr_plan* p, int32_t round_mode, int32_t n_round, const uint8_t* cell_keep, char* err,
+                      size_t errlen) {
+    if (!p) {
+        set_err(err, errlen, "plan is NULL");
+        return IPR_EINVAL;
+    }
+    if (round_mode < 0 || round_mode > 2 || (round_mode != 0 && (n_round < 0 || n_round > 15))) {
+        set_err(err, errlen, "round_mode must be 0, 1 or 2 and n_round in [0, 15]");
+        return IPR_EINVAL;
+    }
+    IPR_CUDA(cudaSetDevice(p->device));
+    p->post_round_mode = round_mode;
+    p->post_p10 = std::pow(10.0, (double)n_round);
+    if (cell_keep) {
+        if (!p->d_cell_keep) IPR_CUDA(dev_malloc(&p->d_cell_keep, (size_t)p->n_cells));
+        IPR_CUDA(cudaMemcpyAsync(p->d_cell_keep, cell_keep, (size_t)p->n_cells, cudaMemcpyHostToDevice, p->stream));
+        IPR_CUDA(cudaStreamSynchronize(p->stream));
+    } else if (p->d_cell_keep) {
+        dev_free(p->d_cell_keep);
+        p->d_cell_keep = nullptr;
+    }
     return IPR_OK;
 }
 
@@ -677,6 +716,7 @@ int ipr_plan_cressman(ipr_plan* p, const double* radii_m, int32_t n_radii, int32
         if ((rc = run_contraction(p, kCressman, wp, false, t0, t1, d_out + (size_t)ri * stack_stride, ld_out, err,
                                   errlen)))
             return rc;
+        if ((rc = run_post(p, t0, t1, d_out + (size_t)ri * stack_stride, ld_out, err, errlen))) return rc;
     }
     return IPR_OK;
 }
@@ -744,6 +784,8 @@ struct HostJob {
     int n_radii;
     double* out;
     bool out_pinned = false;  // caller's output is page-locked: D2H lands in it directly
+    int round_mode = 0, n_round = 0;
+    const uint8_t* cell_keep = nullptr;
 };
 
 constexpr int kRing = 3;
@@ -925,6 +967,9 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
             td.mark("(teardown) plan destroyed");
         }
     } g{plan};
+    if ((job.round_mode != 0 || job.cell_keep) &&
+        (rc = ipr_plan_set_post(plan, job.round_mode, job.n_round, job.cell_keep, err, errlen)))
+        return rc;
     tr.mark("plan created (allocations, coordinate upload, zero-distance scan)");
     rc = plan_set_obs_ld(plan, job.obs + d0, job.n_dates, err, errlen);
     if (rc) return rc;
@@ -1051,6 +1096,33 @@ int ipr_idw_f64(const double* cell_x, const double* cell_y, int64_t n_cells, con
                 int32_t n_st, const double* obs, int32_t n_dates, double p, const int* devices, int n_devices,
                 double* out, char* err, size_t errlen) {
     HostJob job{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, false, p, nullptr, 0, out};
+    return run_host_job(job, devices, n_devices, err, errlen);
+}
+
+int ipr_idw_post_f64(const double* cell_x, const double* cell_y, int64_t n_cells, const double* st_x,
+                     const double* st_y, int32_t n_st, const double* obs, int32_t n_dates, double p, int32_t round_mode,
+                     int32_t n_round, const uint8_t* cell_keep, const int* devices, int n_devices, double* out,
+                     char* err, size_t errlen) {
+    HostJob job{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, false, p, nullptr, 0, out};
+    job.round_mode = round_mode;
+    job.n_round = n_round;
+    job.cell_keep = cell_keep;
+    return run_host_job(job, devices, n_devices, err, errlen);
+}
+
+int ipr_cressman_post_f64(const double* cell_x, const double* cell_y, int64_t n_cells, const double* st_x,
+                          const double* st_y, int32_t n_st, const double* obs, int32_t n_dates,
+                          const double* radii_m, int32_t n_radii, int32_t round_mode, int32_t n_round,
+                          const uint8_t* cell_keep, const int* devices, int n_devices, double* out, char* err,
+                          size_t errlen) {
+    if (!radii_m || n_radii <= 0) {
+        set_err(err, errlen, "radii_m must hold at least one radius");
+        return IPR_EINVAL;
+    }
+    HostJob job{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, true, 2.0, radii_m, n_radii, out};
+    job.round_mode = round_mode;
+    job.n_round = n_round;
+    job.cell_keep = cell_keep;
     return run_host_job(job, devices, n_devices, err, errlen);
 }
 

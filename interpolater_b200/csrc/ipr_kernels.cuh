@@ -514,4 +514,47 @@ __global__ void idw_zero_fix_kernel(const int* __restrict__ fix_cell, const int*
     if (hit > 0) out[(long long)(t - t_lo) * ld_out + fix_cell[i]] = pred;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Optional post-pass on finished layers (the reference's steps right after the hot loop, which would
+// otherwise cost host passes over the whole stack): rounding to n digits — mode 1 = R's round()
+// as used by terra::app(x, function(v) round(v, n)) at R/IDW.R:356-358 (nearest of the floor/ceil
+// candidates at 10^-n, ties to the even candidate); mode 2 = terra's round(SpatRaster, n) at
+// R/Cressman.R:353-355 (std::round(v * 10^n) / 10^n) — and the polygon mask (cells whose centre is
+// outside the study area become NA, R/IDW.R:376-381).  Elementwise, HBM-bound.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double round_r_digits(double x, double p10) {
+    if (!isfinite(x) || x == 0.0) return x;
+    const double ax = fabs(x);
+    const double x10 = p10 * ax;
+    const double i10 = floor(x10);
+    const double xd = i10 / p10;
+    const double xu = ceil(x10) / p10;
+    const double du = xu - ax, dd = ax - xd;
+    const bool even = (fmod(i10, 2.0) == 0.0);
+    const double r = (dd < du || (dd == du && even)) ? xd : xu;
+    return copysign(r, x);
+}
+__device__ __forceinline__ double round_terra_digits(double x, double p10) {
+    if (!isfinite(x)) return x;
+    return round(x * p10) / p10;
+}
+
+__global__ void post_kernel(double* __restrict__ out, long long ld_out, long long n_cells, int n_layers,
+                            int round_mode, double p10, const uint8_t* __restrict__ cell_keep) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const bool keep = (cell_keep == nullptr) || (cell_keep[c] != 0);
+    const double na = __longlong_as_double((long long)kNaRealBits);
+    for (int t = blockIdx.y; t < n_layers; t += gridDim.y) {
+        double* ptr = out + (long long)t * ld_out + c;
+        if (!keep) {
+            *ptr = na;
+            continue;
+        }
+        if (round_mode == 0) continue;
+        const double v = *ptr;
+        *ptr = (round_mode == 1) ? round_r_digits(v, p10) : round_terra_digits(v, p10);
+    }
+}
+
 }  // namespace ipr

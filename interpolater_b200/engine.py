@@ -35,7 +35,22 @@ def _devices(devices):
     return arr, len(devices)
 
 
-def idw_grid(cell_x, cell_y, st_x, st_y, obs, p=2.0, devices=None, out=None):
+ROUND_NONE, ROUND_R, ROUND_TERRA = 0, 1, 2
+
+
+def _post_args(n_round, round_mode, cell_keep, n_cells):
+    if n_round is None:
+        round_mode, n_round = ROUND_NONE, 0
+    keep = None
+    if cell_keep is not None:
+        keep = np.ascontiguousarray(cell_keep, dtype=np.uint8)
+        if keep.shape != (n_cells,):
+            raise ValueError("cell_keep must have one entry per cell")
+    return int(round_mode), int(n_round), keep
+
+
+def idw_grid(cell_x, cell_y, st_x, st_y, obs, p=2.0, devices=None, out=None, n_round=None, round_mode=ROUND_R,
+             cell_keep=None):
     """IDW over every cell x date.  Returns (n_cells, n_dates) float64, Fortran order (one layer
     per date, like the values of a terra stack); NaN (R's NA_real_ payload) where the reference
     yields NA.  Replaces R/IDW.R:249-355."""
@@ -52,13 +67,21 @@ def idw_grid(cell_x, cell_y, st_x, st_y, obs, p=2.0, devices=None, out=None):
         raise ValueError("out must be a Fortran-ordered float64 (n_cells, n_dates) array")
     dev, ndev = _devices(devices)
     err = _native.errbuf()
-    rc = lib.ipr_idw_f64(cx.ctypes.data, cy.ctypes.data, cx.shape[0], sx.ctypes.data, sy.ctypes.data, sx.shape[0],
-                         ob.ctypes.data, n_dates, float(p), dev, ndev, out.ctypes.data, err, _native.ERRLEN)
+    rmode, nr, keep = _post_args(n_round, round_mode, cell_keep, cx.shape[0])
+    if rmode == ROUND_NONE and keep is None:
+        rc = lib.ipr_idw_f64(cx.ctypes.data, cy.ctypes.data, cx.shape[0], sx.ctypes.data, sy.ctypes.data, sx.shape[0],
+                             ob.ctypes.data, n_dates, float(p), dev, ndev, out.ctypes.data, err, _native.ERRLEN)
+    else:
+        rc = lib.ipr_idw_post_f64(cx.ctypes.data, cy.ctypes.data, cx.shape[0], sx.ctypes.data, sy.ctypes.data,
+                                  sx.shape[0], ob.ctypes.data, n_dates, float(p), rmode, nr,
+                                  keep.ctypes.data if keep is not None else None, dev, ndev, out.ctypes.data, err,
+                                  _native.ERRLEN)
     _native.check(rc, err)
     return out
 
 
-def cressman_grid(cell_x, cell_y, st_x, st_y, obs, radii_m, devices=None, out=None):
+def cressman_grid(cell_x, cell_y, st_x, st_y, obs, radii_m, devices=None, out=None, n_round=None,
+                  round_mode=ROUND_TERRA, cell_keep=None):
     """Cressman analysis for each radius (metres, ascending unique).  Returns
     (n_radii, n_cells, n_dates) with each [ri] Fortran-ordered.  Replaces R/Cressman.R:268-345."""
     lib = _native.load()
@@ -78,9 +101,16 @@ def cressman_grid(cell_x, cell_y, st_x, st_y, obs, radii_m, devices=None, out=No
             raise ValueError("out must be a flat float64 array of n_radii*n_cells*n_dates elements")
     dev, ndev = _devices(devices)
     err = _native.errbuf()
-    rc = lib.ipr_cressman_f64(cx.ctypes.data, cy.ctypes.data, n_cells, sx.ctypes.data, sy.ctypes.data, sx.shape[0],
-                              ob.ctypes.data, n_dates, rad.ctypes.data, rad.shape[0], dev, ndev,
-                              flat.ctypes.data, err, _native.ERRLEN)
+    rmode, nr, keep = _post_args(n_round, round_mode, cell_keep, n_cells)
+    if rmode == ROUND_NONE and keep is None:
+        rc = lib.ipr_cressman_f64(cx.ctypes.data, cy.ctypes.data, n_cells, sx.ctypes.data, sy.ctypes.data, sx.shape[0],
+                                  ob.ctypes.data, n_dates, rad.ctypes.data, rad.shape[0], dev, ndev,
+                                  flat.ctypes.data, err, _native.ERRLEN)
+    else:
+        rc = lib.ipr_cressman_post_f64(cx.ctypes.data, cy.ctypes.data, n_cells, sx.ctypes.data, sy.ctypes.data,
+                                       sx.shape[0], ob.ctypes.data, n_dates, rad.ctypes.data, rad.shape[0], rmode, nr,
+                                       keep.ctypes.data if keep is not None else None, dev, ndev, flat.ctypes.data,
+                                       err, _native.ERRLEN)
     _native.check(rc, err)
     # radius-major, each stack column-major (n_cells fastest): view as (n_radii, n_dates, n_cells)^T
     return flat.reshape(rad.shape[0], n_dates, n_cells).transpose(0, 2, 1)

@@ -134,6 +134,20 @@ class GridGeometry:
         cell = row * self.ncol + col
         return np.where(inside, cell, -1)
 
+    def crop_window(self, v: SpatVector):
+        """terra::crop(x, v, snap="out"): the sub-grid covering v's extent snapped outward to cell
+        edges (clipped to this grid).  Returns (sub GridGeometry, indices of its cells in this grid)."""
+        c0 = max(0, int(math.floor((v.xmin - self.xmin) / self.xres + 1e-9)))
+        c1 = min(self.ncol, int(math.ceil((v.xmax - self.xmin) / self.xres - 1e-9)))
+        r0 = max(0, int(math.floor((self.ymax - v.ymax) / self.yres + 1e-9)))
+        r1 = min(self.nrow, int(math.ceil((self.ymax - v.ymin) / self.yres - 1e-9)))
+        if c1 <= c0 or r1 <= r0:
+            raise ValueError("extents do not overlap")
+        sub = GridGeometry(self.xmin + c0 * self.xres, self.xmin + c1 * self.xres, self.ymax - r1 * self.yres,
+                           self.ymax - r0 * self.yres, c1 - c0, r1 - r0, self.crs)
+        cells = (np.arange(r0, r1)[:, None] * self.ncol + np.arange(c0, c1)[None, :]).reshape(-1)
+        return sub, cells
+
     def polygon_cover(self, v: SpatVector):
         """Boolean n_cells mask: cell centre inside the polygon layer (even-odd rule over all rings,
         so holes are honoured) — terra::mask / rasterize with touches=FALSE."""
@@ -202,16 +216,7 @@ class SpatRaster:
     def crop_mask(self, v: SpatVector):
         """terra::mask(terra::crop(x, v, snap="out"), v) (R/IDW.R:376-381): crop to the polygon's
         extent snapped outward to cell edges, then set cells whose centre is outside to NA."""
-        g = self.geom
-        c0 = max(0, int(math.floor((v.xmin - g.xmin) / g.xres + 1e-9)))
-        c1 = min(g.ncol, int(math.ceil((v.xmax - g.xmin) / g.xres - 1e-9)))
-        r0 = max(0, int(math.floor((g.ymax - v.ymax) / g.yres + 1e-9)))
-        r1 = min(g.nrow, int(math.ceil((g.ymax - v.ymin) / g.yres - 1e-9)))
-        if c1 <= c0 or r1 <= r0:
-            raise ValueError("extents do not overlap")
-        sub = GridGeometry(g.xmin + c0 * g.xres, g.xmin + c1 * g.xres, g.ymax - r1 * g.yres, g.ymax - r0 * g.yres,
-                           c1 - c0, r1 - r0, g.crs)
-        cells = (np.arange(r0, r1)[:, None] * g.ncol + np.arange(c0, c1)[None, :]).reshape(-1)
+        sub, cells = self.geom.crop_window(v)
         vals = np.array(self.values[cells, :], order="F", copy=True)
         cover = sub.polygon_cover(v)
         vals[~cover, :] = np.nan

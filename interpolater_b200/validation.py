@@ -254,16 +254,22 @@ def metrics(sim, obs, Rain_threshold=None):
 # --------------------------------------------------------------------------------------
 # .validate  (ICM:215-287)
 # --------------------------------------------------------------------------------------
-def validate(test_cords: pd.DataFrame, test_data: pd.DataFrame, Ensamble, Rain_threshold=None):
+def validate(test_cords: pd.DataFrame, test_data: pd.DataFrame, Ensamble, Rain_threshold=None, sim_pts=None,
+             layer_names=None):
     """Samples the stack at the test stations (cell containing the point; NA outside the raster),
     pairs Obs/Sim per station by date and evaluates metrics().  `Ensamble` is a spatial.SpatRaster
-    whose layers are the sorted unique dates of the run."""
+    whose layers are the sorted unique dates of the run; alternatively the already-extracted
+    (n_test, n_layers) matrix `sim_pts` with its `layer_names` (the engine evaluated just the cells
+    containing the test stations, so the full stack never has to be sampled on the host)."""
     message("Validation process in progress. Please wait.")
     test_cols = [c for c in test_data.columns if c != "Date"]
     # ICM:231: ID := as.numeric(Cod) — factor levels follow test_data's column order, and the
     # i-th test coordinate row is matched to the i-th level (ICM:217, :236)
-    sim_pts = Ensamble.extract(test_cords["X"].to_numpy(dtype=np.float64), test_cords["Y"].to_numpy(dtype=np.float64))
-    layer_dates = list(Ensamble.names)
+    if sim_pts is None:
+        sim_pts = Ensamble.extract(test_cords["X"].to_numpy(dtype=np.float64),
+                                   test_cords["Y"].to_numpy(dtype=np.float64))
+        layer_names = Ensamble.names
+    layer_dates = list(layer_names)
     date_key = [str(d)[:10] for d in pd.to_datetime(test_data["Date"])] if not _is_str_dates(test_data["Date"]) \
         else [str(d) for d in test_data["Date"]]
     pos = {d: i for i, d in enumerate(layer_dates)}

@@ -162,6 +162,48 @@ def test_duplicate_cells_and_all_stations_on_cells():
     assert_parity(engine.idw_grid(cx, cy, sx, sy, obs), ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="dups")
 
 
+def test_device_post_pass_rounding_and_mask():
+    """Rounding (R's round / terra's round) and the polygon mask fused on the device equal the host
+    definitions applied to the un-rounded engine output."""
+    from interpolater_b200 import spatial
+
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(37, 23, 40, 150, na_frac=0.1, all_na_dates=(4,), seed=3)
+    raw = engine.idw_grid(cx, cy, sx, sy, obs)
+    for digits in (0, 1, 2, 3):
+        got = engine.idw_grid(cx, cy, sx, sy, obs, n_round=digits, round_mode=engine.ROUND_R)
+        want = np.array([ref.r_round(v, digits) for v in raw.ravel()]).reshape(raw.shape)
+        assert np.array_equal(got, want, equal_nan=True), f"R round digits={digits}"
+        got_t = engine.idw_grid(cx, cy, sx, sy, obs, n_round=digits, round_mode=engine.ROUND_TERRA)
+        assert np.array_equal(got_t, spatial.terra_round(raw, digits), equal_nan=True), f"terra round {digits}"
+    assert np.array_equal(spatial.r_round(raw, 2), engine.idw_grid(cx, cy, sx, sy, obs, n_round=2), equal_nan=True)
+    keep = (np.arange(cx.size) % 3 != 0).astype(np.uint8)
+    got = engine.idw_grid(cx, cy, sx, sy, obs, n_round=1, cell_keep=keep)
+    want = spatial.r_round(raw, 1)
+    want[keep == 0, :] = np.nan
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.all(got[keep == 0, :].view(np.uint64) == 0x7FF00000000007A2)
+    radii = np.array([6e3, 15e3])
+    rawc = engine.cressman_grid(cx, cy, sx, sy, obs, radii)
+    gotc = engine.cressman_grid(cx, cy, sx, sy, obs, radii, n_round=2, cell_keep=keep)
+    wantc = spatial.terra_round(np.ascontiguousarray(rawc), 2)
+    wantc[:, keep == 0, :] = np.nan
+    assert np.array_equal(np.ascontiguousarray(gotc), wantc, equal_nan=True)
+
+
+def test_idw_mask_equals_crop_mask_of_unmasked_run(packaged):
+    """IDW(Mask=TRUE) computes only the cropped window and masks on the device; it must equal
+    terra::mask(terra::crop(x, shp, snap="out"), shp) applied to the Mask=FALSE stack."""
+    args = dict(BD_Obs=packaged["BD_Obs"], BD_Coord=packaged["BD_Coord"], shapefile=packaged["shapefile"],
+                grid_resolution=2, p=2, n_round=1)
+    full = ipr.IDW(Mask=False, **args)
+    masked = ipr.IDW(Mask=True, **args)
+    want = full.crop_mask(packaged["shapefile"])
+    assert (masked.geom.ncol, masked.geom.nrow) == (want.geom.ncol, want.geom.nrow)
+    assert masked.geom.xmin == want.geom.xmin and masked.geom.ymax == want.geom.ymax
+    assert np.array_equal(masked.values, want.values, equal_nan=True)
+    assert np.isnan(masked.values).any() and not np.isnan(masked.values).all()
+
+
 def test_buffer_pool_release():
     lib = _native.load()
     cx, cy, sx, sy, obs = synthetic.synthetic_case(300, 300, 64, 130)
