@@ -976,20 +976,13 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
     tr.mark("obs uploaded and prepared");
     const int n_stacks = job.cressman ? job.n_radii : 1;
     // Work items: (stack, date chunk), stack outermost so that the A-operand cache is generated once
-    // per radius.  Chunks are whole 128-date granules (256 dates, or 128 when a slot would exceed
-    // ~3 GiB); the first chunk of the block is a single granule so that D2H starts early.
-    const long long gran_bytes = (long long)job.n_cells * 8 * kGran;
-    const int chunk = (2 * gran_bytes > (3LL << 30)) ? kGran : 2 * kGran;
+    // per radius.  A chunk is one 128-date granule (1 GB per 10^6 cells): D2H starts after the first
+    // granule and only the last granule's copy is left when the kernels finish.
+    const int chunk = kGran;
     struct Item { int stack, t0, t1; };
     std::vector<Item> items;
-    for (int s = 0; s < n_stacks; s++) {
-        int t = 0;
-        while (t < nd) {
-            const int len = (s == 0 && t == 0) ? kGran : chunk;
-            items.push_back({s, t, std::min(nd, t + len)});
-            t += len;
-        }
-    }
+    for (int s = 0; s < n_stacks; s++)
+        for (int t = 0; t < nd; t += chunk) items.push_back({s, t, std::min(nd, t + chunk)});
     const size_t slot_doubles = (size_t)job.n_cells * std::min(chunk, (int)round_up(nd, 16));
     IPR_CUDA(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
     PageableSink sink;
@@ -1062,11 +1055,13 @@ int run_host_job(const HostJob& job, const int* devices, int n_devices, char* er
         if (e != cudaSuccess) cudaGetLastError();
         jobx.out_pinned = (e == cudaSuccess && attr.type == cudaMemoryTypeHost);
     }
-    // date blocks: multiples of 128 dates so that tiles stay aligned; remainder to the last devices
+    // contiguous date blocks, as even as possible in units of 32 dates (the width step of the
+    // contraction's tail tiles); every device numbers its own dates from 0, so no other alignment
+    // is needed
     std::vector<int> bounds(G + 1, 0);
     {
-        const int n_blk = (job.n_dates + 127) / 128;
-        for (int g = 0; g <= G; g++) bounds[g] = std::min<long long>(job.n_dates, (long long)n_blk * g / G * 128);
+        const int n_blk = (job.n_dates + 31) / 32;
+        for (int g = 0; g <= G; g++) bounds[g] = (int)std::min<long long>(job.n_dates, (long long)n_blk * g / G * 32);
         bounds[G] = job.n_dates;
     }
     std::vector<int> rcs(G, IPR_OK);

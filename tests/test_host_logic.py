@@ -214,5 +214,7 @@ def test_date_block_bounds():
         b = sharding.date_block_bounds(n, g)
         assert b[0] == 0 and b[-1] == n and len(b) == g + 1
         assert all(b[i] <= b[i + 1] for i in range(g))
-        assert all(x % 128 == 0 for x in b[:-1])
-    assert sharding.date_block_bounds(3650, 8) == [0, 384, 896, 1280, 1792, 2304, 2688, 3200, 3650]
+        assert all(x % 32 == 0 for x in b[:-1])
+    b = sharding.date_block_bounds(3650, 8)
+    assert b == [0, 448, 896, 1376, 1824, 2272, 2752, 3200, 3650]
+    assert max(b[i + 1] - b[i] for i in range(8)) <= 480     # balanced to within one 32-date step

@@ -22,7 +22,7 @@ def _worker(rank, world, port, n_dates, q):
     from oracle import reference_port as ref
 
     cx, cy, sx, sy, obs = synthetic.synthetic_case(6, 5, 7, n_dates, na_frac=0.1, all_na_dates=(1,))
-    b = sharding.date_block_bounds(n_dates, world, align=128)
+    b = sharding.date_block_bounds(n_dates, world)
     lo, hi = b[rank], b[rank + 1]
     block = ref.idw_reference(cx, cy, sx, sy, obs[lo:hi], 2.0) if hi > lo else np.empty((cx.size, 0))
     # timing-style reduction used by bench.py: max over ranks
