@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
     if (n_stages > 0) {
         const double* w0 = wsrc + (size_t)__ldg(list) * kWStageDoubles;
 #pragma unroll
-        for (int kk = 0; kk < kKSteps; kk++) w_cur[kk] = __ldcs(w0 + kk * kThreads);
+        for (int kk = 0; kk < kKSteps; kk++) w_cur[kk] = __ldg(w0 + kk * kThreads);
     }
 
     for (int it = 0; it < n_stages; it++) {
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
             const int itn = (it + 1 < n_stages) ? it + 1 : it;
             const double* wn = wsrc + (size_t)__ldg(list + itn) * kWStageDoubles;
 #pragma unroll
-            for (int kk = 0; kk < kKSteps; kk++) w_next[kk] = __ldcs(wn + kk * kThreads);
+            for (int kk = 0; kk < kKSteps; kk++) w_next[kk] = __ldg(wn + kk * kThreads);
         }
         mbar_wait(&full_bar[slot], j & 1);
 #pragma unroll
@@ -411,7 +411,9 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
                 if (fl == 1) v = na;        // R/IDW.R:299-301 all-NA date
                 else if (fl == 2) v = 0.0;  // R/IDW.R:294-297 all |obs| < 1e-12
             }
-            args.out[(long long)(t - args.t_lo) * args.ld_out + cell] = v;
+            // streaming store: the output is written once and never re-read by this kernel, so it must
+            // not displace the L2-resident B operand and the A tiles shared by concurrent CTAs
+            __stcs(&args.out[(long long)(t - args.t_lo) * args.ld_out + cell], v);
         }
     }
 }
