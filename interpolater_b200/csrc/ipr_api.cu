@@ -194,6 +194,7 @@ struct ipr_plan {
     int* d_stage_list = nullptr;  // per cell tile of the chunk: stages with any non-zero weight
     int* d_n_active = nullptr;
     int* d_perm = nullptr;        // spatial (Morton) order of the stations: sorted position -> input index
+    int* d_run_perm = nullptr;    // Morton order of the 8-cell runs: 8 consecutive entries = one compact cell tile
     unsigned long long* d_active_total = nullptr;
     unsigned long long stage_tiles_total = 0;  // (cell tile, stage) blocks the dense product would visit
     int w_chunk_tiles = 0;   // capacity of d_wfrag in cell tiles
@@ -245,6 +246,7 @@ int ensure_weights(ipr_plan* p, int mode, const WeightParams& wp, int tile0, int
     w.stage_list = p->d_stage_list;
     w.n_active = p->d_n_active;
     w.active_total = p->d_active_total;
+    w.run_perm = (mode == kCressman) ? p->d_run_perm : nullptr;
     p->stage_tiles_total += (unsigned long long)n_tiles * p->n_stages;
     w.cell_tile0 = tile0;
     w.n_cell_tiles = n_tiles;
@@ -302,6 +304,7 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
         a.wsum = p->d_wsum;
         a.stage_list = p->d_stage_list;
         a.n_active = p->d_n_active;
+        a.run_perm = (mode == kCressman) ? p->d_run_perm : nullptr;
         a.z0 = p->d_z0;
         a.mask = p->d_mask;
         a.date_flag = idw ? p->d_flag : nullptr;
@@ -535,6 +538,7 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     PLAN_CUDA(dev_malloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
     PLAN_CUDA(dev_malloc(&p->d_wsum, sizeof(double) * p->c_pad));
     PLAN_CUDA(dev_malloc(&p->d_perm, sizeof(int) * n_st));
+    PLAN_CUDA(dev_malloc(&p->d_run_perm, sizeof(int) * (size_t)(p->c_pad / 8)));
     PLAN_CUDA(dev_malloc(&p->d_active_total, sizeof(unsigned long long)));
     PLAN_CUDA(cudaMemsetAsync(p->d_active_total, 0, sizeof(unsigned long long), p->stream));
     PLAN_CUDA(cudaMemsetAsync(p->d_z0, 0, sizeof(double) * p->z_doubles, p->stream));
@@ -553,6 +557,21 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
             }
         }
         PLAN_CUDA(cudaMemcpyAsync(p->d_cell, h.data(), sizeof(double2) * p->c_pad, cudaMemcpyHostToDevice, p->stream));
+        // cell tiles for Cressman: 8 Morton-consecutive runs of 8 consecutive cells, i.e. compact
+        // 2-D patches instead of 64 x 1 strips, so that fewer station stages reach any cell of a tile
+        std::vector<int> run_perm;
+        {
+            const int n_runs = (int)(p->c_pad / 8);
+            std::vector<double> rx(n_runs), ry(n_runs);
+            for (int i = 0; i < n_runs; i++) {
+                rx[i] = h[(size_t)i * 8].x;
+                ry[i] = h[(size_t)i * 8].y;
+            }
+            run_perm = morton_order(rx.data(), ry.data(), n_runs);
+        }
+        PLAN_CUDA(cudaMemcpyAsync(p->d_run_perm, run_perm.data(), sizeof(int) * run_perm.size(), cudaMemcpyHostToDevice,
+                                  p->stream));
+        PLAN_CUDA(cudaStreamSynchronize(p->stream));
         for (int i = 0; i < n_st; i++) {
             if (!std::isfinite(st_x[i]) || !std::isfinite(st_y[i])) {
                 ipr_plan_destroy(p);
@@ -601,6 +620,7 @@ void ipr_plan_destroy(ipr_plan* p) {
     dev_free(p->d_stage_list);
     dev_free(p->d_n_active);
     dev_free(p->d_perm);
+    dev_free(p->d_run_perm);
     dev_free(p->d_cell_keep);
     dev_free(p->d_active_total);
     if (p->ev0) cudaEventDestroy(p->ev0);

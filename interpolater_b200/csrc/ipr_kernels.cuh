@@ -76,6 +76,8 @@ struct ContractArgs {
     const double* wsum;       // [c_pad] per-cell sum of weights over all stations
     const int* stage_list;    // [n_cell_tiles][n_stages] stages holding any non-zero weight, ascending
     const int* n_active;      // [n_cell_tiles] length of each list
+    const int* run_perm;      // nullptr, or [c_pad/8]: warp w of cell tile T owns the 8 consecutive cells
+                              // of run run_perm[8T + w] (spatially compact tiles for Cressman)
     const double* z0;         // granule blocks [n_gran][n_stages][kBlkDoubles]
     const double* mask;       // same layout (masked variants only)
     const uint8_t* date_flag; // IDW: 0 normal, 1 all-NA layer, 2 exact-zero layer; nullptr for Cressman
@@ -95,6 +97,7 @@ struct WeightArgs {
     double* wsum;             // [c_pad]
     int* stage_list;          // [n_cell_tiles][n_stages]
     int* n_active;            // [n_cell_tiles]
+    const int* run_perm;      // see ContractArgs
     unsigned long long* active_total;  // cumulative count of active (cell tile, stage) blocks
     int cell_tile0, n_cell_tiles;
     int n_stages;
@@ -225,7 +228,8 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
     const int q = lane & 3;   // station inside the k-step (A column)
     const int r = lane >> 2;  // cell row of the fragment
     const int ct = args.cell_tile0 + blockIdx.x;
-    const long long cell = (long long)ct * kCellsPerCta + warp * 8 + r;
+    const long long run = args.run_perm ? (long long)__ldg(args.run_perm + (size_t)ct * 8 + warp) : (long long)ct * 8 + warp;
+    const long long cell = run * 8 + r;
     const double2 cxy = args.cell_xy[cell];
     double* dst = args.wfrag + (size_t)blockIdx.x * args.n_stages * kWStageDoubles + threadIdx.x;
     int* list = args.stage_list + (size_t)blockIdx.x * args.n_stages;
@@ -316,7 +320,9 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
 
     const int q = lane & 3;   // k index inside a k-step (A column / B row)
     const int r = lane >> 2;  // row of the 8x8 fragment (cell) / B column
-    const long long cell = (long long)(args.cell_tile0 + ct_local) * kCellsPerCta + warp * 8 + r;
+    const long long ct = args.cell_tile0 + ct_local;
+    const long long run = args.run_perm ? (long long)__ldg(args.run_perm + (size_t)ct * 8 + warp) : ct * 8 + warp;
+    const long long cell = run * 8 + r;
     const double* wsrc = args.wfrag + (size_t)ct_local * args.n_stages * kWStageDoubles + threadIdx.x;
 
     double acc[2 * NP][2];
