@@ -194,6 +194,7 @@ struct ipr_plan {
     int* d_stage_list = nullptr;  // per cell tile of the chunk: stages with any non-zero weight
     int* d_n_active = nullptr;
     int* d_perm = nullptr;        // spatial (Morton) order of the stations: sorted position -> input index
+    double4* d_stage_box = nullptr;  // bounding box of each station stage (Cressman culling in weights_kernel)
     int* d_run_perm = nullptr;    // Morton order of the 8-cell runs: 8 consecutive entries = one compact cell tile
     unsigned long long* d_active_total = nullptr;
     unsigned long long stage_tiles_total = 0;  // (cell tile, stage) blocks the dense product would visit
@@ -247,6 +248,7 @@ int ensure_weights(ipr_plan* p, int mode, const WeightParams& wp, int tile0, int
     w.n_active = p->d_n_active;
     w.active_total = p->d_active_total;
     w.run_perm = (mode == kCressman) ? p->d_run_perm : nullptr;
+    w.stage_box = (mode == kCressman) ? p->d_stage_box : nullptr;
     p->stage_tiles_total += (unsigned long long)n_tiles * p->n_stages;
     w.cell_tile0 = tile0;
     w.n_cell_tiles = n_tiles;
@@ -539,6 +541,7 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     PLAN_CUDA(dev_malloc(&p->d_wsum, sizeof(double) * p->c_pad));
     PLAN_CUDA(dev_malloc(&p->d_perm, sizeof(int) * n_st));
     PLAN_CUDA(dev_malloc(&p->d_run_perm, sizeof(int) * (size_t)(p->c_pad / 8)));
+    PLAN_CUDA(dev_malloc(&p->d_stage_box, sizeof(double4) * (size_t)p->n_stages));
     PLAN_CUDA(dev_malloc(&p->d_active_total, sizeof(unsigned long long)));
     PLAN_CUDA(cudaMemsetAsync(p->d_active_total, 0, sizeof(unsigned long long), p->stream));
     PLAN_CUDA(cudaMemsetAsync(p->d_z0, 0, sizeof(double) * p->z_doubles, p->stream));
@@ -586,6 +589,22 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
         std::vector<double2> hs(p->s_pad + kKT, make_double2(kPadCoord, kPadCoord));
         for (int i = 0; i < n_st; i++) hs[i] = make_double2(canon_zero(st_x[perm[i]]), canon_zero(st_y[perm[i]]));
         PLAN_CUDA(cudaMemcpyAsync(p->d_perm, perm.data(), sizeof(int) * n_st, cudaMemcpyHostToDevice, p->stream));
+        std::vector<double4> boxes(p->n_stages);
+        for (int st = 0; st < p->n_stages; st++) {
+            double4 b = make_double4(hs[(size_t)st * kKT].x, hs[(size_t)st * kKT].y, hs[(size_t)st * kKT].x,
+                                     hs[(size_t)st * kKT].y);
+            for (int k = 1; k < kKT; k++) {
+                const double2 c = hs[(size_t)st * kKT + k];
+                b.x = std::min(b.x, c.x);
+                b.y = std::min(b.y, c.y);
+                b.z = std::max(b.z, c.x);
+                b.w = std::max(b.w, c.y);
+            }
+            boxes[st] = b;
+        }
+        PLAN_CUDA(cudaMemcpyAsync(p->d_stage_box, boxes.data(), sizeof(double4) * boxes.size(), cudaMemcpyHostToDevice,
+                                  p->stream));
+        PLAN_CUDA(cudaStreamSynchronize(p->stream));
         PLAN_CUDA(cudaMemcpyAsync(p->d_st, hs.data(), sizeof(double2) * hs.size(), cudaMemcpyHostToDevice, p->stream));
         PLAN_CUDA(cudaStreamSynchronize(p->stream));  // staging vectors go out of scope
     }
@@ -621,6 +640,7 @@ void ipr_plan_destroy(ipr_plan* p) {
     dev_free(p->d_n_active);
     dev_free(p->d_perm);
     dev_free(p->d_run_perm);
+    dev_free(p->d_stage_box);
     dev_free(p->d_cell_keep);
     dev_free(p->d_active_total);
     if (p->ev0) cudaEventDestroy(p->ev0);

@@ -98,6 +98,8 @@ struct WeightArgs {
     int* stage_list;          // [n_cell_tiles][n_stages]
     int* n_active;            // [n_cell_tiles]
     const int* run_perm;      // see ContractArgs
+    const double4* stage_box; // nullptr, or [n_stages] bounding box (xmin, ymin, xmax, ymax) of each stage's
+                              // stations: Cressman skips stages whose box is farther than R from the tile's
     unsigned long long* active_total;  // cumulative count of active (cell tile, stage) blocks
     int cell_tile0, n_cell_tiles;
     int n_stages;
@@ -235,12 +237,46 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
     int* list = args.stage_list + (size_t)blockIdx.x * args.n_stages;
     double wsum[4] = {0.0, 0.0, 0.0, 0.0};
     if (threadIdx.x == 0) s_n_active = 0;
+    // bounding box of the tile's cells (Cressman culling)
+    __shared__ double s_box[kConsumerWarps][4];
+    double bx0 = cxy.x, bx1 = cxy.x, by0 = cxy.y, by1 = cxy.y;
+    if (WMODE == kCressman && args.stage_box != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bx0 = fmin(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+            bx1 = fmax(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+            by0 = fmin(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+            by1 = fmax(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+        }
+        if (lane == 0) {
+            s_box[warp][0] = bx0;
+            s_box[warp][1] = bx1;
+            s_box[warp][2] = by0;
+            s_box[warp][3] = by1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w8 = 0; w8 < kConsumerWarps; w8++) {
+            bx0 = fmin(bx0, s_box[w8][0]);
+            bx1 = fmax(bx1, s_box[w8][1]);
+            by0 = fmin(by0, s_box[w8][2]);
+            by1 = fmax(by1, s_box[w8][3]);
+        }
+    }
     for (int st0 = 0; st0 < args.n_stages; st0 += kChunkStages) {
         const int ns = min(kChunkStages, args.n_stages - st0);
         __syncthreads();
         for (int i = threadIdx.x; i < ns * kKT; i += kThreads) s_st[i] = args.st_xy[st0 * kKT + i];
         __syncthreads();
         for (int sl = 0; sl < ns; sl++) {
+            if (WMODE == kCressman && args.stage_box != nullptr) {
+                // every station of the stage farther than R from every cell of the tile (box-to-box
+                // distance, with a safety margin): all weights are exactly 0 -> nothing to do
+                const double4 b = args.stage_box[st0 + sl];
+                const double gx = fmax(0.0, fmax(b.x - bx1, bx0 - b.z));
+                const double gy = fmax(0.0, fmax(b.y - by1, by0 - b.w));
+                if (gx * gx + gy * gy > args.wp.a * (1.0 + 1e-9)) continue;
+            }
             double w[kKSteps];
             bool any = false;
             // independent reciprocal chains overlap; fixed summation order per k-step residue
