@@ -181,7 +181,13 @@ struct ipr_plan {
     int* d_fix_off = nullptr;
     int* d_fix_st = nullptr;
     long long zero_pairs = 0;
-    std::vector<uint8_t> h_has_na;
+    std::vector<uint8_t> h_has_na;     // per date: the date's granule needs the masked contraction
+    // sparse-NA correction (granules with few missing observations are contracted unmasked)
+    int* d_na_n = nullptr;
+    int* d_na_idx = nullptr;
+    uint8_t* d_date_mode = nullptr;    // 1: denominator of this date is corrected by idw_sparse_na_fix_kernel
+    std::vector<uint8_t> h_date_mode;
+    bool any_sparse_fix = false;
     bool obs_ready = false;
     long long launches = 0;
     // optional post-pass (rounding, polygon mask) applied to every finished layer
@@ -433,15 +439,50 @@ int prepare_obs(ipr_plan* p, char* err, size_t errlen) {
                                                    p->n_stages, p->d_flag, p->d_has_na, p->d_counters + 1);
     IPR_CUDA(cudaGetLastError());
     p->launches++;
+    {
+        const int warps_per_block = 8;
+        na_lists_kernel<<<(p->n_dates + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, p->stream>>>(
+            p->d_obs, p->n_dates, p->n_dates, p->n_st, p->d_perm, p->d_na_n, p->d_na_idx);
+        IPR_CUDA(cudaGetLastError());
+        p->launches++;
+    }
     int bad = 0;
     p->h_has_na.resize(p->n_dates);
+    std::vector<int> na_n(p->n_dates);
     IPR_CUDA(cudaMemcpyAsync(p->h_has_na.data(), p->d_has_na, p->n_dates, cudaMemcpyDeviceToHost, p->stream));
+    IPR_CUDA(cudaMemcpyAsync(na_n.data(), p->d_na_n, sizeof(int) * p->n_dates, cudaMemcpyDeviceToHost, p->stream));
     IPR_CUDA(cudaMemcpyAsync(&bad, p->d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     IPR_CUDA(cudaStreamSynchronize(p->stream));
     if (bad) {
         set_err(err, errlen, "obs holds %d infinite value(s); only finite observations or NA are supported", bad);
         return IPR_EUNSUPPORTED;
     }
+    // Per 128-date granule: few missing observations (<= 5 % of the entries, <= kNaCap per date) ->
+    // unmasked contraction + denominator correction of the affected dates; otherwise masked GEMM.
+    // (regenerating a missing weight costs ~10 FP64 instructions against 1 FMA per entry of the
+    // masked GEMM, so the break-even is near 10 % NA.)
+    p->h_date_mode.assign(p->n_dates, 0);
+    p->any_sparse_fix = false;
+    const bool allow_sparse = !(getenv("IPR_SPARSE_NA") && atoi(getenv("IPR_SPARSE_NA")) == 0);
+    for (int g0 = 0; g0 < p->n_dates; g0 += kGran) {
+        const int g1 = std::min(p->n_dates, g0 + kGran);
+        long long total = 0;
+        int worst = 0;
+        for (int t = g0; t < g1; t++) {
+            total += na_n[t];
+            worst = std::max(worst, na_n[t]);
+        }
+        if (total == 0 || !allow_sparse || worst > kNaCap || total * 20 > (long long)(g1 - g0) * p->n_st) continue;
+        for (int t = g0; t < g1; t++) {
+            p->h_has_na[t] = 0;
+            if (na_n[t] > 0) {
+                p->h_date_mode[t] = 1;
+                p->any_sparse_fix = true;
+            }
+        }
+    }
+    IPR_CUDA(cudaMemcpyAsync(p->d_date_mode, p->h_date_mode.data(), p->n_dates, cudaMemcpyHostToDevice, p->stream));
+    IPR_CUDA(cudaStreamSynchronize(p->stream));
     p->obs_ready = true;
     return IPR_OK;
 }
@@ -536,6 +577,9 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     PLAN_CUDA(dev_malloc(&p->d_mask, sizeof(double) * p->z_doubles));
     PLAN_CUDA(dev_malloc(&p->d_flag, (size_t)p->n_gran * kGran));
     PLAN_CUDA(dev_malloc(&p->d_has_na, (size_t)p->n_gran * kGran));
+    PLAN_CUDA(dev_malloc(&p->d_na_n, sizeof(int) * (size_t)n_dates));
+    PLAN_CUDA(dev_malloc(&p->d_na_idx, sizeof(int) * (size_t)n_dates * kNaCap));
+    PLAN_CUDA(dev_malloc(&p->d_date_mode, (size_t)n_dates));
     PLAN_CUDA(dev_malloc(&p->d_counters, sizeof(int) * 4));
     PLAN_CUDA(dev_malloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
     PLAN_CUDA(dev_malloc(&p->d_wsum, sizeof(double) * p->c_pad));
@@ -629,6 +673,9 @@ void ipr_plan_destroy(ipr_plan* p) {
     dev_free(p->d_mask);
     dev_free(p->d_flag);
     dev_free(p->d_has_na);
+    dev_free(p->d_na_n);
+    dev_free(p->d_na_idx);
+    dev_free(p->d_date_mode);
     dev_free(p->d_counters);
     dev_free(p->d_pairs);
     dev_free(p->d_fix_cell);
@@ -700,6 +747,25 @@ int ipr_plan_idw(ipr_plan* p, double pw, int32_t t0, int32_t t1, double* d_out, 
         wp.a = -half;
     }
     if ((rc = run_contraction(p, mode, wp, true, t0, t1, d_out, ld_out, err, errlen))) return rc;
+    bool fix_here = false;
+    if (p->any_sparse_fix)
+        for (int t = t0; t < t1 && !fix_here; t++) fix_here = (p->h_date_mode[t] == 1);
+    if (fix_here) {
+        const int threads = 256;
+        for (int tb = t0; tb < t1; tb += 32768) {
+            const int te = std::min(t1, tb + 32768);
+            dim3 grid((unsigned)((p->n_cells + threads - 1) / threads), (unsigned)(te - tb));
+            double* o = d_out + (size_t)(tb - t0) * ld_out;
+#define IPR_FIX_ARGS p->d_cell, p->d_st, p->s_pad, p->d_wsum, p->n_cells, p->d_na_n, p->d_na_idx, p->d_date_mode, \
+                     p->d_flag, tb, te, wp, o, ld_out
+            if (mode == kIdwP2) idw_sparse_na_fix_kernel<kIdwP2><<<grid, threads, 0, p->stream>>>(IPR_FIX_ARGS);
+            else if (mode == kIdwEvenP) idw_sparse_na_fix_kernel<kIdwEvenP><<<grid, threads, 0, p->stream>>>(IPR_FIX_ARGS);
+            else idw_sparse_na_fix_kernel<kIdwGenericP><<<grid, threads, 0, p->stream>>>(IPR_FIX_ARGS);
+#undef IPR_FIX_ARGS
+            IPR_CUDA(cudaGetLastError());
+            p->launches++;
+        }
+    }
     if (p->n_fix > 0) {
         dim3 grid((unsigned)((t1 - t0 + 127) / 128), (unsigned)p->n_fix);
         idw_zero_fix_kernel<<<grid, 128, 0, p->stream>>>(p->d_fix_cell, p->d_fix_off, p->d_fix_st, p->n_fix, p->d_obs,

@@ -559,6 +559,89 @@ __global__ void idw_zero_fix_kernel(const int* __restrict__ fix_cell, const int*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sparse-NA IDW.  When a 128-date granule holds only a few missing observations, the second GEMM
+// (weights x availability mask) is not worth its 2*S flop per cell-day: the granule is contracted
+// unmasked (numerator / wsum) and the denominator of the few affected dates is corrected,
+//     out = numer / (wsum - sum_{s NA on t} w(c,s)),
+// with the missing stations' weights regenerated on the fly (~10 FP64 instructions each, i.e.
+// 10 * NA-fraction of the cost of the masked GEMM).  Lists are built in station order by one warp
+// per date, so the summation order is deterministic.
+// ---------------------------------------------------------------------------------------------
+constexpr int kNaCap = 256;   // most NA stations per date the correction handles
+
+__global__ void na_lists_kernel(const double* __restrict__ obs, long long ld_obs, int n_dates, int n_st,
+                                const int* __restrict__ perm, int* __restrict__ na_n, int* __restrict__ na_idx) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= n_dates) return;
+    int count = 0;
+    for (int s0 = 0; s0 < n_st; s0 += 32) {
+        const int s = s0 + lane;
+        bool isna = false;
+        if (s < n_st) {
+            const double v = obs[(long long)perm[s] * ld_obs + t];
+            isna = (v != v);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, isna);
+        if (isna) {
+            const int pos = count + __popc(m & ((1u << lane) - 1u));
+            if (pos < kNaCap) na_idx[(size_t)t * kNaCap + pos] = s;
+        }
+        count += __popc(m);
+    }
+    if (lane == 0) na_n[t] = count;
+}
+
+template <int WMODE>
+__global__ void idw_sparse_na_fix_kernel(const double2* __restrict__ cell_xy, const double2* __restrict__ st_xy,
+                                         int s_pad, const double* __restrict__ wsum, long long n_cells,
+                                         const int* __restrict__ na_n, const int* __restrict__ na_idx,
+                                         const uint8_t* __restrict__ date_mode, const uint8_t* __restrict__ date_flag,
+                                         int t_lo, int t_hi, WeightParams wp, double* __restrict__ out,
+                                         long long ld_out) {
+    __shared__ double2 s_na[kNaCap];
+    __shared__ int s_idx[kNaCap];
+    const int t = t_lo + blockIdx.y;
+    if (t >= t_hi || date_mode[t] != 1 || date_flag[t] != 0) return;   // uniform per block
+    const int n = na_n[t];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int s = na_idx[(size_t)t * kNaCap + k];
+        s_idx[k] = s;
+        s_na[k] = st_xy[s];
+    }
+    __syncthreads();
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const double2 cxy = cell_xy[c];
+    double corr = 0.0;
+    for (int k = 0; k < n; k++) {
+        const double dx = cxy.x - s_na[k].x, dy = cxy.y - s_na[k].y;
+        corr += weight_from_d2<WMODE>(fma(dy, dy, dx * dx), wp);
+    }
+    const double ws = wsum[c];
+    double denom = ws - corr;
+    if (corr > 0.99 * ws) {
+        // the missing stations carry almost all of the weight: the subtraction would cancel, so sum
+        // the weights of the available stations directly (rare: a missing station next to the cell)
+        denom = 0.0;
+        int k = 0;
+        for (int s = 0; s < s_pad; s++) {
+            if (k < n && s_idx[k] == s) {
+                k++;
+                continue;
+            }
+            const double2 sc = st_xy[s];
+            const double dx = cxy.x - sc.x, dy = cxy.y - sc.y;
+            denom += weight_from_d2<WMODE>(fma(dy, dy, dx * dx), wp);
+        }
+    }
+    double* ptr = out + (long long)(t - t_lo) * ld_out + c;
+    double v = (*ptr) * ws / denom;     // numer = (numer / wsum) * wsum
+    if (!isfinite(v) || denom == 0.0) v = __longlong_as_double((long long)kNaRealBits);
+    *ptr = v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Optional post-pass on finished layers (the reference's steps right after the hot loop, which would
 // otherwise cost host passes over the whole stack): rounding to n digits — mode 1 = R's round()
 // as used by terra::app(x, function(v) round(v, n)) at R/IDW.R:356-358 (nearest of the floor/ceil

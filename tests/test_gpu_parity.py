@@ -204,6 +204,37 @@ def test_idw_mask_equals_crop_mask_of_unmasked_run(packaged):
     assert np.isnan(masked.values).any() and not np.isnan(masked.values).all()
 
 
+def test_sparse_na_correction_matches_masked_gemm_and_oracle(monkeypatch):
+    """Granules with few NA are contracted unmasked and their denominators corrected; the result must
+    agree with the masked-GEMM path and with the oracle, including when a missing station carries
+    almost all of a cell's weight (the correction then sums the available weights directly)."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(33, 21, 90, 300, na_frac=0.02, plant_zero_dist=2, seed=17)
+    sx[5], sy[5] = cx[100] + 1e-3, cy[100]          # a millimetre from a cell centre: w ~ 1e6
+    obs[10:40, 5] = np.nan                           # ... and missing on 30 dates
+    obs[200, :] = np.nan                             # an all-NA date inside a sparse granule
+    obs[0:2, 0] = np.nan                             # co-located (planted) station missing
+    want = ref.idw_reference(cx, cy, sx, sy, obs, 2.0)
+    monkeypatch.setenv("IPR_SPARSE_NA", "1")
+    plan = engine.Plan(0, cx, cy, sx, sy, 300)
+    plan.set_obs(obs)
+    l0 = plan.launch_count
+    import torch
+    o = torch.empty((300, cx.size), dtype=torch.float64, device="cuda")
+    plan.idw(o.data_ptr(), 2.0)
+    plan.sync()
+    sparse = o.cpu().numpy().T
+    plan.close()
+    monkeypatch.setenv("IPR_SPARSE_NA", "0")
+    dense = engine.idw_grid(cx, cy, sx, sy, obs)
+    assert_parity(sparse, want, label="sparse-NA path")
+    assert_parity(dense, want, label="masked-GEMM path")
+    assert_parity(sparse, dense, tol=1e-12, label="sparse vs masked")
+    for p in (3.0, 4.0):
+        monkeypatch.setenv("IPR_SPARSE_NA", "1")
+        a = engine.idw_grid(cx, cy, sx, sy, obs, p=p)
+        assert_parity(a, ref.idw_reference(cx, cy, sx, sy, obs, p), label=f"sparse p={p}")
+
+
 def test_buffer_pool_release():
     lib = _native.load()
     cx, cy, sx, sy, obs = synthetic.synthetic_case(300, 300, 64, 130)
