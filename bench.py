@@ -188,10 +188,19 @@ def cpu_reference_sample(a, threads, steps=1):
         return t1 - t0, (t2 - t1) / nd
 
     setup_s, date_s = [], []
+    # BLAS itself single-threaded (R's reference BLAS is); with threads > 1 the
+    # parallelism is the pool over dates, so `cores` is exactly the number of busy threads
+    try:
+        from threadpoolctl import threadpool_limits
+        blas_limit = threadpool_limits(limits=1)
+    except Exception:
+        blas_limit = None
     for _ in range(steps):
         s_, d_ = one_pass()
         setup_s.append(s_)
         date_s.append(d_)
+    if blas_limit is not None:
+        blas_limit.restore_original_limits()
     ref.LONG_DOUBLE_ROWSUMS = True
     setup = float(np.mean(setup_s))
     per_date = float(np.mean(date_s))
