@@ -116,6 +116,47 @@ __global__ void k_mix(double* out, int iters, double a0, double b0) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// legacy warp-level tensor paths (mma.sync): headroom for error-free low-precision emulation of
+// the 0/1 mask contraction (INT8 / BF16 slices with exact accumulation)
+template <int NACC>
+__global__ void k_imma(int* out, int iters, int a0, int b0) {
+    int c[NACC][4];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) { c[i][0] = threadIdx.x; c[i][1] = i; c[i][2] = 1; c[i][3] = 2; }
+    unsigned a[4] = {(unsigned)a0, (unsigned)a0 + 1, (unsigned)a0 + 2, (unsigned)a0 + threadIdx.x};
+    unsigned b[2] = {(unsigned)b0, (unsigned)b0 * 3};
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < NACC; i++)
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+r"(c[i][0]), "+r"(c[i][1]), "+r"(c[i][2]), "+r"(c[i][3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int NACC>
+__global__ void k_hmma_bf16(float* out, int iters, unsigned a0, unsigned b0) {
+    float c[NACC][4];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) { c[i][0] = threadIdx.x; c[i][1] = i; c[i][2] = 1; c[i][3] = 2; }
+    unsigned a[4] = {a0, a0 + 1, a0 + 2, a0 + threadIdx.x};
+    unsigned b[2] = {b0, b0 * 3};
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < NACC; i++)
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // reciprocal variants -------------------------------------------------------
 __device__ __forceinline__ double rcp_mufu2(double x) {  // MUFU.RCP64H seed + 2 Newton steps
     double r;
@@ -226,6 +267,16 @@ int main() {
         float ms16 = time_ms([&] { k_mix<16, 16><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
         float ms32 = time_ms([&] { k_mix<16, 32><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
         printf("MIX 16 DMMA + {0,8,16,32} DFMA per iter, 8 warps/SM: %.3f %.3f %.3f %.3f ms\n", ms0, ms8, ms16, ms32);
+    }
+    // ---- legacy mma.sync INT8 / BF16 (warp-level tensor path)
+    for (int wps : {8, 16, 32}) {
+        int threads = 128, blocks = nsm * wps * 32 / threads;
+        float ms = time_ms([&] { k_imma<8><<<blocks, threads>>>((int*)out, iters, 3, 5); });
+        double ops = 2.0 * 16 * 8 * 32 * 8 * iters * (double)blocks * threads / 32;
+        printf("IMMA m16n8k32 s8 nacc=8 warps/SM=%2d : %.3f ms  %.1f TOP/s\n", wps, ms, ops / ms * 1e-9);
+        ms = time_ms([&] { k_hmma_bf16<8><<<blocks, threads>>>((float*)out, iters, 0x3f803f80u, 0x3f803f80u); });
+        ops = 2.0 * 16 * 8 * 16 * 8 * iters * (double)blocks * threads / 32;
+        printf("HMMA m16n8k16 bf16 nacc=8 warps/SM=%2d : %.3f ms  %.1f TFLOP/s\n", wps, ms, ops / ms * 1e-9);
     }
     // ---- reciprocal variants: accuracy and cost
     {
