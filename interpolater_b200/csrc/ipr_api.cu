@@ -555,7 +555,7 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     p->n_st = n_st;
     p->s_pad = (int)round_up(n_st, kKT);
     p->n_dates = n_dates;
-    p->n_gran = (int)((n_dates + kGran - 1) / kGran) + 1;  // +1: a 256-date tile may start on the last granule
+    p->n_gran = (int)((n_dates + kGran - 1) / kGran) + 1;  // +1 spare granule of zero padding
     p->n_stages = p->s_pad / kKT;
     p->z_doubles = (size_t)p->n_gran * p->n_stages * kBlkDoubles;
     p->pair_capacity = std::max(4 * n_st, 65536);
