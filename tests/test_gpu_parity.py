@@ -134,6 +134,22 @@ def test_randomised_shapes_against_oracle(seed):
         assert_parity(got[i], want[i], label=f"cressman seed={seed} R={radii[i]}")
 
 
+def test_long_record_on_a_small_grid():
+    """Many dates (several launches of <= 56 date tiles each), few cells and stations — the shape of
+    the packaged fixture stretched in time; mixes NA-free, sparse-NA and NA-heavy granules."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(6, 4, 9, 9000, seed=41)
+    rng = np.random.default_rng(41)
+    obs[2000:2400][rng.random((400, 9)) < 0.3] = np.nan      # NA-heavy stretch -> masked GEMM
+    obs[5000:5010, 2] = np.nan                                # a few NA -> corrected denominators
+    obs[7777, :] = np.nan
+    assert_parity(engine.idw_grid(cx, cy, sx, sy, obs), ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="D=9000")
+    radii = np.array([1500.0, 4000.0])
+    got = engine.cressman_grid(cx, cy, sx, sy, obs, radii)
+    want = ref.cressman_reference(cx, cy, sx, sy, obs, radii)
+    for i in range(2):
+        assert_parity(got[i], want[i], label=f"D=9000 cressman {i}")
+
+
 def test_many_stations_and_wide_station_extent():
     """More stations than one shared-memory chunk of the weight kernel (1024) and stations far
     outside the grid (Morton order must cope with a bounding box much larger than the raster)."""
