@@ -360,6 +360,12 @@ def run_ours(a):
         "output_stream_gbs": n_stacks * C * D * 8 / (ms_kernel * 1e-3) * 1e-9,
         # `achieved` counts the DENSE product as SURVEY 8(d) prescribes; what the tensor pipe really
         # executed is reported beside it (equal for IDW)
+        # masked IDW: SURVEY 8(d) counts 4*S flop per cell-day (numerator + mask GEMM); the mask GEMM
+        # runs error-free on the INTEGER tensor pipe (8-bit digit planes of the weights), so only
+        # 2*S of them load the FP64 pipe and `frac` can exceed 1
+        "mask_gemm_pipe": ("int8 (mma.sync u8, exact)" if a.workload == "idw_masked"
+                           and os.environ.get("IPR_MASK_INT8", "1") != "0" else
+                           ("fp64" if a.workload == "idw_masked" else None)),
         "executed_block_frac": executed_frac,
         "executed_tflops": achieved * executed_frac,
         "executed_frac_of_peak": achieved * executed_frac / peaks["dmma_tflops"],

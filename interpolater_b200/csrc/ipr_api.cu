@@ -190,6 +190,19 @@ struct ipr_plan {
     bool any_sparse_fix = false;
     bool obs_ready = false;
     long long launches = 0;
+    // error-free int8 contraction of the availability mask (IPR_MASK_INT8=0 disables): digit planes of the
+    // weights, byte mask, list of (cell, date) pairs that need a direct FP64 evaluation
+    bool int8_mask = false;
+    int n_kblocks = 0;
+    double* d_wmax = nullptr;
+    uint4* d_wq = nullptr;
+    unsigned char* d_mask8 = nullptr;
+    int2* d_fb_list = nullptr;
+    int* d_fb_count = nullptr;
+    int fb_cap = 1 << 22;
+    int wq_mode = -1;
+    double wq_param = 0.0;
+    int wq_tile0 = -1;
     // optional post-pass (rounding, polygon mask) applied to every finished layer
     int post_round_mode = 0;
     double post_p10 = 1.0;
@@ -250,6 +263,7 @@ int ensure_weights(ipr_plan* p, int mode, const WeightParams& wp, int tile0, int
     w.st_xy = p->d_st;
     w.wfrag = p->d_wfrag;
     w.wsum = p->d_wsum;
+    w.wmax = p->d_wmax;
     w.stage_list = p->d_stage_list;
     w.n_active = p->d_n_active;
     w.active_total = p->d_active_total;
@@ -282,7 +296,7 @@ int ensure_wcache(ipr_plan* p, char* err, size_t errlen) {
     const size_t tile_bytes = (size_t)p->n_stages * kWStageDoubles * sizeof(double);
     size_t free_b = 0, total_b = 0;
     IPR_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = free_b / 2;
+    size_t budget = free_b / (p->int8_mask ? 3 : 2);   // the digit planes take as much again as the weights
     if (const char* e = getenv("IPR_WCACHE_MB")) budget = (size_t)atoll(e) << 20;
     long long tiles = std::min<long long>(total_tiles, (long long)(budget / tile_bytes));
     if (tiles < 1) {
@@ -293,6 +307,137 @@ int ensure_wcache(ipr_plan* p, char* err, size_t errlen) {
     IPR_CUDA(dev_malloc(&p->d_stage_list, sizeof(int) * (size_t)tiles * p->n_stages));
     IPR_CUDA(dev_malloc(&p->d_n_active, sizeof(int) * (size_t)tiles));
     p->w_chunk_tiles = (int)tiles;
+    if (p->int8_mask)
+        IPR_CUDA(dev_malloc(&p->d_wq, sizeof(uint4) * (size_t)tiles * p->n_kblocks * kQTileKbU4));
+    return IPR_OK;
+}
+
+template <int NP>
+int launch_contract_denom(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles, char* err, size_t errlen) {
+    using L = SmemLayout<false>;
+    static bool configured[64] = {false};
+    auto kern = contract_kernel<NP, false, true>;
+    if (!configured[p->device & 63]) {
+        IPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        configured[p->device & 63] = true;
+    }
+    for (size_t i0 = 0; i0 < tiles.size(); i0 += kMaxTilesPerLaunch) {
+        const int n = (int)std::min<size_t>(kMaxTilesPerLaunch, tiles.size() - i0);
+        a.tiles.n = n;
+        for (int i = 0; i < n; i++) a.tiles.t0[i] = tiles[i0 + i];
+        kern<<<(unsigned)((long long)a.n_cell_tiles * n), kThreads, L::kTotal, p->stream>>>(a);
+        IPR_CUDA(cudaGetLastError());
+        p->launches++;
+    }
+    return IPR_OK;
+}
+
+// Masked granules of [t0, t1) for the current cell-tile chunk: digit planes of the weights (cached
+// like the weights), integer mask contraction into the output buffer, numerator GEMM dividing by
+// it, direct re-evaluation of the listed ill-scaled pairs.
+int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs& a, const TileSets& ts, int t0, int t1,
+                    char* err, size_t errlen) {
+    const double key = (mode == kIdwEvenP) ? (double)wp.n : wp.a;
+    if (!(p->wq_mode == mode && p->wq_param == key && p->wq_tile0 == a.cell_tile0)) {
+        WeightArgs w{};
+        w.cell_xy = p->d_cell;
+        w.st_xy = p->d_st;
+        w.cell_tile0 = a.cell_tile0;
+        w.n_cell_tiles = a.n_cell_tiles;
+        w.n_stages = p->n_stages;
+        w.wp = wp;
+        if (mode == kIdwP2)
+            slice_weights_kernel<kIdwP2><<<a.n_cell_tiles, 256, 0, p->stream>>>(w, p->d_wmax, p->d_wq, p->n_kblocks);
+        else if (mode == kIdwEvenP)
+            slice_weights_kernel<kIdwEvenP><<<a.n_cell_tiles, 256, 0, p->stream>>>(w, p->d_wmax, p->d_wq, p->n_kblocks);
+        else
+            slice_weights_kernel<kIdwGenericP><<<a.n_cell_tiles, 256, 0, p->stream>>>(w, p->d_wmax, p->d_wq,
+                                                                                     p->n_kblocks);
+        IPR_CUDA(cudaGetLastError());
+        p->launches++;
+        p->wq_mode = mode;
+        p->wq_param = key;
+        p->wq_tile0 = a.cell_tile0;
+    }
+    // granules (128 dates) covered by the masked half tiles, with the width needed inside the window
+    std::vector<int> gran[9];
+    {
+        std::vector<int> starts;
+        for (int np : {4, 2})
+            for (int h : ts.m[np]) starts.push_back(h - h % kGran);
+        std::sort(starts.begin(), starts.end());
+        starts.erase(std::unique(starts.begin(), starts.end()), starts.end());
+        for (int b : starts) {
+            const int used = std::min(b + kGran, t1) - b;
+            gran[used > 96 ? 8 : used > 64 ? 6 : used > 32 ? 4 : 2].push_back(b);
+        }
+    }
+    IPR_CUDA(cudaMemsetAsync(p->d_fb_count, 0, sizeof(int), p->stream));
+    {
+        static bool configured[64] = {false};
+        if (!configured[p->device & 63]) {
+            IPR_CUDA(cudaFuncSetAttribute(denom_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenomSmemBytes));
+            configured[p->device & 63] = true;
+        }
+    }
+    DenomArgs d{};
+    d.wq = p->d_wq;
+    d.mask8 = p->d_mask8;
+    d.wmax = p->d_wmax;
+    d.date_flag = p->d_flag;
+    d.out = a.out;
+    d.ld_out = a.ld_out;
+    d.n_cells = p->n_cells;
+    d.cell_tile0 = a.cell_tile0;
+    d.n_cell_tiles = a.n_cell_tiles;
+    d.n_kblocks = p->n_kblocks;
+    d.t_lo = t0;
+    d.t_hi = t1;
+    d.fb_list = p->d_fb_list;
+    d.fb_count = p->d_fb_count;
+    d.fb_cap = p->fb_cap;
+    int rc;
+    for (int np : {8, 6, 4, 2}) {
+        const std::vector<int>& tiles = gran[np];
+        for (size_t i0 = 0; i0 < tiles.size(); i0 += kMaxTilesPerLaunch) {
+            const int n = (int)std::min<size_t>(kMaxTilesPerLaunch, tiles.size() - i0);
+            d.tiles.n = n;
+            for (int i = 0; i < n; i++) d.tiles.t0[i] = tiles[i0 + i];
+            denom_imma_kernel<<<(unsigned)((long long)a.n_cell_tiles * n), kThreads, kDenomSmemBytes, p->stream>>>(d);
+            IPR_CUDA(cudaGetLastError());
+            p->launches++;
+        }
+    }
+    if (!gran[8].empty() && (rc = launch_contract_denom<8>(p, a, gran[8], err, errlen))) return rc;
+    if (!gran[6].empty() && (rc = launch_contract_denom<6>(p, a, gran[6], err, errlen))) return rc;
+    if (!gran[4].empty() && (rc = launch_contract_denom<4>(p, a, gran[4], err, errlen))) return rc;
+    if (!gran[2].empty() && (rc = launch_contract_denom<2>(p, a, gran[2], err, errlen))) return rc;
+    {
+        const int warps = 1 << 12;  // list entries handled per launch wave; the kernel bounds itself by the count
+        const unsigned blocks = (unsigned)((p->fb_cap + 7) / 8);
+        (void)warps;
+#define IPR_DF_ARGS p->d_fb_list, p->d_fb_count, p->fb_cap, p->d_cell, p->d_st, p->n_st, p->d_perm, p->d_obs, \
+                    (long long)p->n_dates, wp, t0, a.out, a.ld_out
+        // launched over a modest grid and looped: the list is almost always empty
+        int n_fb = 0;
+        IPR_CUDA(cudaMemcpyAsync(&n_fb, p->d_fb_count, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        IPR_CUDA(cudaStreamSynchronize(p->stream));
+        if (n_fb > p->fb_cap) {
+            set_err(err, errlen, "%d ill-scaled (cell, date) pairs exceed the int8 mask path's list (%d); "
+                    "set IPR_MASK_INT8=0", n_fb, p->fb_cap);
+            return IPR_EUNSUPPORTED;
+        }
+        if (n_fb > 0) {
+            const unsigned nb = (unsigned)((n_fb + 7) / 8);
+            (void)blocks;
+            if (mode == kIdwP2) idw_direct_fix_kernel<kIdwP2><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
+            else if (mode == kIdwEvenP) idw_direct_fix_kernel<kIdwEvenP><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
+            else idw_direct_fix_kernel<kIdwGenericP><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
+            IPR_CUDA(cudaGetLastError());
+            p->launches++;
+        }
+#undef IPR_DF_ARGS
+    }
     return IPR_OK;
 }
 
@@ -324,6 +469,13 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
         a.n_stages = p->n_stages;
         a.t_lo = t0;
         a.t_hi = t1;
+        // masked granules through the error-free int8 mask contraction (opt-in)
+        const bool use_int8 = idw && p->int8_mask && (!ts.m[4].empty() || !ts.m[2].empty());
+        if (use_int8) {
+            if ((rc = run_int8_masked(p, mode, wp, a, ts, t0, t1, err, errlen))) return rc;
+            ts.m[4].clear();
+            ts.m[2].clear();
+        }
         if (!ts.u[8].empty() && (rc = launch_contract<8, false>(p, a, ts.u[8], err, errlen))) return rc;
         if (!ts.u[6].empty() && (rc = launch_contract<6, false>(p, a, ts.u[6], err, errlen))) return rc;
         if (!ts.u[4].empty() && (rc = launch_contract<4, false>(p, a, ts.u[4], err, errlen))) return rc;
@@ -443,6 +595,14 @@ int prepare_obs(ipr_plan* p, char* err, size_t errlen) {
         const int warps_per_block = 8;
         na_lists_kernel<<<(p->n_dates + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, p->stream>>>(
             p->d_obs, p->n_dates, p->n_dates, p->n_st, p->d_perm, p->d_na_n, p->d_na_idx);
+        IPR_CUDA(cudaGetLastError());
+        p->launches++;
+    }
+    if (p->int8_mask) {
+        const long long total = (long long)p->n_gran * p->n_kblocks * 16 * 32;
+        prep_mask8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(
+            p->d_obs, p->n_dates, p->n_dates, p->n_st, p->d_perm, reinterpret_cast<uint2*>(p->d_mask8), p->n_kblocks,
+            p->n_gran);
         IPR_CUDA(cudaGetLastError());
         p->launches++;
     }
@@ -571,7 +731,9 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     PLAN_CUDA(cudaEventCreate(&p->ev0));
     PLAN_CUDA(cudaEventCreate(&p->ev1));
     PLAN_CUDA(dev_malloc(&p->d_cell, sizeof(double2) * p->c_pad));
-    PLAN_CUDA(dev_malloc(&p->d_st, sizeof(double2) * (p->s_pad + kKT)));
+    // padded so that both the 16-station stages and the 32-station integer k-blocks stay in bounds
+    const size_t st_alloc = (size_t)std::max<long long>(p->s_pad + kKT, round_up((p->s_pad + kQKb - 1) / kQKb, kM8Kbs) * kQKb);
+    PLAN_CUDA(dev_malloc(&p->d_st, sizeof(double2) * st_alloc));
     PLAN_CUDA(dev_malloc(&p->d_obs, sizeof(double) * (size_t)n_dates * n_st));
     PLAN_CUDA(dev_malloc(&p->d_z0, sizeof(double) * p->z_doubles));
     PLAN_CUDA(dev_malloc(&p->d_mask, sizeof(double) * p->z_doubles));
@@ -583,6 +745,14 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     PLAN_CUDA(dev_malloc(&p->d_counters, sizeof(int) * 4));
     PLAN_CUDA(dev_malloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
     PLAN_CUDA(dev_malloc(&p->d_wsum, sizeof(double) * p->c_pad));
+    PLAN_CUDA(dev_malloc(&p->d_wmax, sizeof(double) * p->c_pad));
+    p->n_kblocks = (int)round_up((p->s_pad + kQKb - 1) / kQKb, kM8Kbs);   // padded: whole pipeline stages
+    p->int8_mask = !(getenv("IPR_MASK_INT8") && atoi(getenv("IPR_MASK_INT8")) == 0);   // default on
+    if (p->int8_mask) {
+        PLAN_CUDA(dev_malloc(&p->d_mask8, (size_t)p->n_gran * p->n_kblocks * kM8BlkBytes));
+        PLAN_CUDA(dev_malloc(&p->d_fb_list, sizeof(int2) * (size_t)p->fb_cap));
+        PLAN_CUDA(dev_malloc(&p->d_fb_count, sizeof(int)));
+    }
     PLAN_CUDA(dev_malloc(&p->d_perm, sizeof(int) * n_st));
     PLAN_CUDA(dev_malloc(&p->d_run_perm, sizeof(int) * (size_t)(p->c_pad / 8)));
     PLAN_CUDA(dev_malloc(&p->d_stage_box, sizeof(double4) * (size_t)p->n_stages));
@@ -630,7 +800,7 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
         // blob, so that for Cressman most (cell tile, stage) blocks lie wholly beyond the radius and
         // are skipped.  The permutation only changes the order of summation.
         std::vector<int> perm = morton_order(st_x, st_y, n_st);
-        std::vector<double2> hs(p->s_pad + kKT, make_double2(kPadCoord, kPadCoord));
+        std::vector<double2> hs(st_alloc, make_double2(kPadCoord, kPadCoord));
         for (int i = 0; i < n_st; i++) hs[i] = make_double2(canon_zero(st_x[perm[i]]), canon_zero(st_y[perm[i]]));
         PLAN_CUDA(cudaMemcpyAsync(p->d_perm, perm.data(), sizeof(int) * n_st, cudaMemcpyHostToDevice, p->stream));
         std::vector<double4> boxes(p->n_stages);
@@ -683,6 +853,11 @@ void ipr_plan_destroy(ipr_plan* p) {
     dev_free(p->d_fix_st);
     dev_free(p->d_wfrag);
     dev_free(p->d_wsum);
+    dev_free(p->d_wmax);
+    dev_free(p->d_wq);
+    dev_free(p->d_mask8);
+    dev_free(p->d_fb_list);
+    dev_free(p->d_fb_count);
     dev_free(p->d_stage_list);
     dev_free(p->d_n_active);
     dev_free(p->d_perm);

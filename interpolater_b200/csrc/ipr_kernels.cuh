@@ -95,6 +95,7 @@ struct WeightArgs {
     const double2* st_xy;     // [s_pad]
     double* wfrag;            // chunk base
     double* wsum;             // [c_pad]
+    double* wmax;             // [c_pad] largest weight of the cell (row scale of the int8 slices)
     int* stage_list;          // [n_cell_tiles][n_stages]
     int* n_active;            // [n_cell_tiles]
     const int* run_perm;      // see ContractArgs
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
     double* dst = args.wfrag + (size_t)blockIdx.x * args.n_stages * kWStageDoubles + threadIdx.x;
     int* list = args.stage_list + (size_t)blockIdx.x * args.n_stages;
     double wsum[4] = {0.0, 0.0, 0.0, 0.0};
+    double wmx = 0.0;
     if (threadIdx.x == 0) s_n_active = 0;
     // bounding box of the tile's cells (Cressman culling)
     __shared__ double s_box[kConsumerWarps][4];
@@ -286,6 +288,7 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
                 const double dx = cxy.x - s.x, dy = cxy.y - s.y;
                 w[kk] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp);
                 wsum[kk & 3] += w[kk];
+                wmx = fmax(wmx, w[kk]);
                 any |= (w[kk] != 0.0);
             }
             // a stage whose 64 x kKT weights are all zero (Cressman: every station beyond R) is not
@@ -302,7 +305,12 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
     // lanes of a quad share the cell; their partial sums cover disjoint stations
     tot += __shfl_xor_sync(0xffffffffu, tot, 1);
     tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-    if (q == 0) args.wsum[cell] = tot;
+    wmx = fmax(wmx, __shfl_xor_sync(0xffffffffu, wmx, 1));
+    wmx = fmax(wmx, __shfl_xor_sync(0xffffffffu, wmx, 2));
+    if (q == 0) {
+        args.wsum[cell] = tot;
+        args.wmax[cell] = wmx;
+    }
     if (threadIdx.x == 0) {
         args.n_active[blockIdx.x] = s_n_active;
         atomicAdd(args.active_total, (unsigned long long)s_n_active);
@@ -317,8 +325,9 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
 // grid.x = n_cell_tiles * n_tiles, date tile fastest: CTAs that run together share the A tile
 // through L2 and the whole B operand (tens of MB) stays L2-resident.
 // ---------------------------------------------------------------------------------------------
-template <int NP, bool MASKED>
+template <int NP, bool MASKED, bool DENOM_IN_OUT = false>
 __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArgs args) {
+    static_assert(!(MASKED && DENOM_IN_OUT), "the denominator comes either from the mask GEMM or from the output buffer");
     using L = SmemLayout<MASKED>;
     constexpr int kStages = L::kStages;
     static_assert(NP >= 1 && NP <= (MASKED ? 4 : 8), "64 accumulator registers per thread");
@@ -443,9 +452,12 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
             const int f = 2 * i + (e & 1);
             const int c = e >> 1;
             const double numer = acc[f][c];
-            const double denom = MASKED ? accm[f][c] : wsum;
+            double* optr = &args.out[(long long)(t - args.t_lo) * args.ld_out + cell];
+            // DENOM_IN_OUT: the per-date denominator was left in the output buffer by
+            // denom_imma_kernel (error-free int8 mask contraction) and is replaced by the result
+            const double denom = MASKED ? accm[f][c] : (DENOM_IN_OUT ? *optr : wsum);
             // date-independent denominator: one true division per thread (inv_wsum), then multiplies
-            double v = MASKED ? numer / denom : numer * inv_wsum;
+            double v = (MASKED || DENOM_IN_OUT) ? numer / denom : numer * inv_wsum;
             // R/IDW.R:332,339 ; R/Cressman.R:317 : !is.finite(v) | denom == 0 -> NA
             if (!isfinite(v) || denom == 0.0) v = na;
             if (args.date_flag != nullptr) {
@@ -455,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
             }
             // streaming store: the output is written once and never re-read by this kernel, so it must
             // not displace the L2-resident B operand and the A tiles shared by concurrent CTAs
-            __stcs(&args.out[(long long)(t - args.t_lo) * args.ld_out + cell], v);
+            __stcs(optr, v);
         }
     }
 }
@@ -639,6 +651,284 @@ __global__ void idw_sparse_na_fix_kernel(const double2* __restrict__ cell_xy, co
     double v = (*ptr) * ws / denom;     // numer = (numer / wsum) * wsum
     if (!isfinite(v) || denom == 0.0) v = __longlong_as_double((long long)kNaRealBits);
     *ptr = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Error-free int8 contraction of the availability mask (IDW with many NA).
+//   denom[c,t] = sum_s w(c,s) m(s,t),  m in {0,1}
+// is the second GEMM of the masked path.  m is exact in 8 bits, so the weights are cut into
+// kQSlices 8-bit digits below a per-cell power-of-two scale, w = 2^e_c * sum_i d_i 256^-(i+1), each
+// digit plane is contracted with the mask on the INTEGER tensor pipe (mma.sync m16n8k32 u8 x u8 ->
+// s32: the sums, at most 2000*255, are exact) and the planes are recombined in FP64.  The integer
+// pipe runs 31x faster than the FP64 one on B200 (profiles/r01_fp64_probe.log), so the eight plane
+// GEMMs cost a fraction of the FP64 GEMM they replace.  Truncation below 2^(e_c-64) bounds the error
+// by S * 2^-64 of the scale; (cell, date) pairs whose denominator is so small against the scale
+// that this exceeds 1e-9 of it (the cell's heaviest stations all missing) are listed and recomputed
+// directly by idw_direct_fix_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kQSlices = 8;
+constexpr int kQKb = 32;                                   // stations per integer k-block
+constexpr int kQTileKbU4 = kQSlices * 4 * 32;              // uint4 per (64-cell tile, k-block)
+constexpr int kM8BlkBytes = 16 * 32 * 8;                   // mask bytes per (granule, k-block), B-fragment order
+constexpr int kM8Kbs = 4;                                  // k-blocks per pipeline stage (one 16 KB bulk copy)
+constexpr int kM8Stages = 3;
+
+struct DenomArgs {
+    const uint4* wq;           // [n_cell_tiles][kQSlices][n_kblocks][4 m-frags][32 lanes]
+    const unsigned char* mask8;  // [n_gran][n_kblocks][kM8BlkBytes]
+    const double* wmax;        // [c_pad]
+    const uint8_t* date_flag;
+    double* out;
+    long long ld_out, n_cells;
+    int cell_tile0, n_cell_tiles, n_kblocks;
+    int t_lo, t_hi;
+    int2* fb_list;             // (cell, date) pairs to recompute directly
+    int* fb_count;
+    int fb_cap;
+    TileList tiles;            // granule start dates
+};
+
+__device__ __forceinline__ void imma_u8(int (&c)[4], const uint4& a, const uint2& b) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y));
+}
+
+// power-of-two scale of a cell's weights: 2^e > wmax (0 when the row has no weight at all)
+__device__ __forceinline__ int row_exponent(double wmax) {
+    return (wmax > 0.0 && isfinite(wmax)) ? ilogb(wmax) + 1 : 0;
+}
+
+// digit planes of the weights in IMMA A-fragment order.  One CTA per 64-cell tile; threads
+// (half, m-frag, lane): half selects the parity of the k-blocks the thread works on.
+template <int WMODE>
+__global__ void __launch_bounds__(256) slice_weights_kernel(const WeightArgs args, const double* __restrict__ wmax,
+                                                            uint4* __restrict__ wq, int n_kblocks) {
+    const int half = threadIdx.x >> 7;
+    const int mf = (threadIdx.x >> 5) & 3;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const long long cell_a = (long long)(args.cell_tile0 + blockIdx.x) * kCellsPerCta + mf * 16 + g;
+    const long long cell_b = cell_a + 8;
+    const double2 ca = args.cell_xy[cell_a], cb = args.cell_xy[cell_b];
+    const double sa = scalbn(1.0, -row_exponent(wmax[cell_a]));
+    const double sb = scalbn(1.0, -row_exponent(wmax[cell_b]));
+    uint4* dst = wq + (size_t)blockIdx.x * n_kblocks * kQTileKbU4 + mf * 32 + lane;
+    for (int kb = half; kb < n_kblocks; kb += 2) {
+        double x[16];  // a0: row a, k = 4q..4q+3 | a1: row b, same k | a2: row a, k+16 | a3: row b, k+16
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const double2 s0 = __ldg(&args.st_xy[kb * kQKb + q * 4 + i]);
+            const double2 s1 = __ldg(&args.st_xy[kb * kQKb + q * 4 + i + 16]);
+            double dx = ca.x - s0.x, dy = ca.y - s0.y;
+            x[i] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp) * sa;
+            dx = cb.x - s0.x, dy = cb.y - s0.y;
+            x[4 + i] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp) * sb;
+            dx = ca.x - s1.x, dy = ca.y - s1.y;
+            x[8 + i] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp) * sa;
+            dx = cb.x - s1.x, dy = cb.y - s1.y;
+            x[12 + i] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp) * sb;
+        }
+#pragma unroll
+        for (int sl = 0; sl < kQSlices; sl++) {
+            unsigned r[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                x[j] *= 256.0;                       // exact (power of two)
+                const int d = (int)x[j];             // 0..255: x in [0, 1) before the scaling
+                x[j] -= (double)d;                   // exact
+                r[j >> 2] |= (unsigned)d << (8 * (j & 3));
+            }
+            dst[((size_t)sl * n_kblocks + kb) * 128] = make_uint4(r[0], r[1], r[2], r[3]);
+        }
+    }
+}
+
+// availability mask as bytes in IMMA B-fragment order (one thread = one lane's 8 bytes)
+__global__ void prep_mask8_kernel(const double* __restrict__ obs, long long ld_obs, int n_dates, int n_st,
+                                  const int* __restrict__ perm, uint2* __restrict__ mask8, int n_kblocks,
+                                  int n_gran) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n_gran * n_kblocks * 16 * 32;
+    if (idx >= total) return;
+    const int lane = (int)(idx & 31);
+    const int j = (int)((idx >> 5) & 15);
+    const long long blk = idx >> 9;               // granule * n_kblocks + kb
+    const int kb = (int)(blk % n_kblocks);
+    const int gran = (int)(blk / n_kblocks);
+    const int t = gran * kGran + j * 8 + (lane >> 2);
+    unsigned b[2] = {0u, 0u};
+    if (t < n_dates) {
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int k = kb * kQKb + (lane & 3) * 4 + i + 16 * hh;
+                if (k < n_st) {
+                    const double v = obs[(long long)perm[k] * ld_obs + t];
+                    if (v == v) b[hh] |= 1u << (8 * i);
+                }
+            }
+    }
+    mask8[idx] = make_uint2(b[0], b[1]);
+}
+
+// denominators of one granule (128 dates) for a 64-cell tile: 8 warps = 2 (32 cells) x 4 (32 dates).
+// n_kblocks is a multiple of kM8Kbs (both operands are padded with zeros).
+__global__ void __launch_bounds__(kThreads, 2) denom_imma_kernel(const DenomArgs args) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    constexpr int kMaskBytes = kM8Kbs * kM8BlkBytes;       // 16 KB: mask bytes of 4 k-blocks
+    constexpr int kABytes = kM8Kbs * 4 * 32 * 16;          // 8 KB: one digit plane of the tile's weights
+    constexpr int kStageBytes = kMaskBytes + kABytes;
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(dsm + kM8Stages * kStageBytes);
+    int* s_release = reinterpret_cast<int*>(s_full + kM8Stages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp & 1, wn = warp >> 1;
+    const int g = lane >> 2, q = lane & 3;
+    const int tile_t0 = args.tiles.t0[blockIdx.x % args.tiles.n];
+    const int ct_local = blockIdx.x / args.tiles.n;
+    const int gran = tile_t0 / kGran;
+    const int nkb = args.n_kblocks;
+    const int nst = nkb / kM8Kbs;          // pipeline stages per digit plane
+    const int total = kQSlices * nst;      // the mask is re-streamed once per digit plane
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kM8Stages; s++) {
+            mbar_init(&s_full[s], 1);
+            s_release[s] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const uint4* wq_tile = args.wq + (size_t)ct_local * kQSlices * nkb * 128;
+    auto produce = [&](int pos) {
+        const int slot = pos % kM8Stages;
+        const int st = pos % nst, sl = pos / nst;   // stages inner, digit planes outer
+        unsigned char* stage = dsm + slot * kStageBytes;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&s_full[slot], kStageBytes);
+        bulk_g2s(stage, args.mask8 + ((size_t)gran * nkb + (size_t)st * kM8Kbs) * kM8BlkBytes, kMaskBytes, &s_full[slot]);
+        bulk_g2s(stage + kMaskBytes, wq_tile + ((size_t)sl * nkb + (size_t)st * kM8Kbs) * 128, kABytes, &s_full[slot]);
+    };
+    if (threadIdx.x == 0)
+        for (int pos = 0; pos < kM8Stages && pos < total; pos++) produce(pos);
+
+    int iacc[2][4][4];
+    double dacc[2][4][4];
+#pragma unroll
+    for (int m = 0; m < 2; m++)
+#pragma unroll
+        for (int n = 0; n < 4; n++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                iacc[m][n][e] = 0;
+                dacc[m][n][e] = 0.0;
+            }
+    double plane_scale = 1.0 / 256.0;
+    int st = 0;
+    for (int pos = 0; pos < total; pos++) {
+        const int slot = pos % kM8Stages;
+        const unsigned char* stage = dsm + slot * kStageBytes;
+        mbar_wait(&s_full[slot], (pos / kM8Stages) & 1);
+#pragma unroll
+        for (int u = 0; u < kM8Kbs; u++) {
+            // A fragments: m-frags 2wm, 2wm+1 ; B fragments: n-frags 4wn .. 4wn+3
+            const uint4* asrc = reinterpret_cast<const uint4*>(stage + kMaskBytes) + (u * 4 + 2 * wm) * 32 + lane;
+            const uint4 a0 = asrc[0], a1 = asrc[32];
+            const uint2* bsrc = reinterpret_cast<const uint2*>(stage + u * kM8BlkBytes) + (wn * 4) * 32 + lane;
+#pragma unroll
+            for (int n = 0; n < 4; n++) {
+                const uint2 b = bsrc[n * 32];
+                imma_u8(iacc[0][n], a0, b);
+                imma_u8(iacc[1][n], a1, b);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&s_release[slot], 1) == kConsumerWarps - 1) {
+                s_release[slot] = 0;
+                __threadfence_block();
+                if (pos + kM8Stages < total) produce(pos + kM8Stages);
+            }
+        }
+        if (++st == nst) {
+            // end of a digit plane: its exact integer sums enter the FP64 accumulators
+            st = 0;
+#pragma unroll
+            for (int m = 0; m < 2; m++)
+#pragma unroll
+                for (int n = 0; n < 4; n++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        dacc[m][n][e] = fma((double)iacc[m][n][e], plane_scale, dacc[m][n][e]);
+                        iacc[m][n][e] = 0;
+                    }
+            plane_scale *= 1.0 / 256.0;
+        }
+    }
+
+    // store: c0,c1 -> row g, dates 2q, 2q+1 ; c2,c3 -> row g+8
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+#pragma unroll
+        for (int hrow = 0; hrow < 2; hrow++) {
+            const long long cell = (long long)(args.cell_tile0 + ct_local) * kCellsPerCta + (2 * wm + m) * 16 + g + 8 * hrow;
+            if (cell >= args.n_cells) continue;
+            const double scale = scalbn(1.0, row_exponent(args.wmax[cell]));
+#pragma unroll
+            for (int n = 0; n < 4; n++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int t = tile_t0 + (wn * 4 + n) * 8 + q * 2 + e;
+                    if (t < args.t_lo || t >= args.t_hi) continue;
+                    const double d = dacc[m][n][2 * hrow + e];
+                    args.out[(long long)(t - args.t_lo) * args.ld_out + cell] = d * scale;
+                    // truncation error <= S * 2^-64 (of the scale): not below 1e-9 of d when d < 2^-22
+                    if (d < 0x1p-22 && args.date_flag[t] == 0) {
+                        const int slot = atomicAdd(args.fb_count, 1);
+                        if (slot < args.fb_cap) args.fb_list[slot] = make_int2((int)cell, t);
+                    }
+                }
+        }
+    }
+}
+constexpr int kDenomSmemBytes = kM8Stages * (kM8Kbs * kM8BlkBytes + kM8Kbs * 4 * 32 * 16) + kM8Stages * 8 + kM8Stages * 4 + 16;
+
+// direct FP64 evaluation of listed (cell, date) pairs: one warp each
+template <int WMODE>
+__global__ void idw_direct_fix_kernel(const int2* __restrict__ list, const int* __restrict__ count, int cap,
+                                      const double2* __restrict__ cell_xy, const double2* __restrict__ st_xy,
+                                      int n_st, const int* __restrict__ perm, const double* __restrict__ obs,
+                                      long long ld_obs, WeightParams wp, int t_lo, double* __restrict__ out,
+                                      long long ld_out) {
+    const int n = min(*count, cap);
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const int2 it = list[w];
+    const double2 c = cell_xy[it.x];
+    double num = 0.0, den = 0.0;
+    for (int s = lane; s < n_st; s += 32) {
+        const double z = obs[(long long)perm[s] * ld_obs + it.y];
+        if (z != z) continue;
+        const double2 sc = st_xy[s];
+        const double dx = c.x - sc.x, dy = c.y - sc.y;
+        const double wgt = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), wp);
+        num = fma(wgt, z, num);
+        den += wgt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        num += __shfl_xor_sync(0xffffffffu, num, o);
+        den += __shfl_xor_sync(0xffffffffu, den, o);
+    }
+    if (lane == 0) {
+        double v = num / den;
+        if (!isfinite(v) || den == 0.0) v = __longlong_as_double((long long)kNaRealBits);
+        out[(long long)(it.y - t_lo) * ld_out + it.x] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

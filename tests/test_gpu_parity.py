@@ -251,6 +251,38 @@ def test_sparse_na_correction_matches_masked_gemm_and_oracle(monkeypatch):
         assert_parity(a, ref.idw_reference(cx, cy, sx, sy, obs, p), label=f"sparse p={p}")
 
 
+def test_int8_mask_contraction_matches_fp64_and_oracle(monkeypatch):
+    """Default path (IPR_MASK_INT8=0 disables): the availability-mask GEMM runs error-free on the integer tensor pipe (8-bit
+    digit planes of the weights); same 1e-9 bar against the oracle, and agreement with the FP64
+    masked GEMM far below it, including a cell whose dominant station is missing (direct re-evaluation)."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(29, 23, 75, 300, na_frac=0.25, plant_zero_dist=2,
+                                                   all_na_dates=(17,), all_zero_dates=(33,), seed=23)
+    sx[7], sy[7] = cx[200] + 1e-4, cy[200]        # 0.1 mm from a cell centre: w ~ 1e8 against ~1e-7 for the rest
+    obs[50:120, 7] = np.nan
+    want = ref.idw_reference(cx, cy, sx, sy, obs, 2.0)
+    monkeypatch.setenv("IPR_MASK_INT8", "0")
+    fp64 = engine.idw_grid(cx, cy, sx, sy, obs)
+    monkeypatch.setenv("IPR_MASK_INT8", "1")
+    int8 = engine.idw_grid(cx, cy, sx, sy, obs)
+    assert_parity(fp64, want, label="fp64 masked")
+    assert_parity(int8, want, label="int8 masked")
+    assert_parity(int8, fp64, tol=1e-11, label="int8 vs fp64 masked")
+    assert np.all(int8[:, 33] == 0.0) and np.all(np.isnan(int8[:, 17]))
+    for p in (1.0, 4.0):
+        assert_parity(engine.idw_grid(cx, cy, sx, sy, obs, p=p), ref.idw_reference(cx, cy, sx, sy, obs, p),
+                      label=f"int8 masked p={p}")
+    # ragged windows through the plan API
+    import torch
+    plan = engine.Plan(0, cx, cy, sx, sy, 300)
+    plan.set_obs(obs)
+    o = torch.full((300, cx.size), -1.0, dtype=torch.float64, device="cuda")
+    for lo, hi in [(0, 70), (70, 257), (257, 300)]:
+        plan.idw(o[lo:].data_ptr(), 2.0, t0=lo, t1=hi)
+    plan.sync()
+    assert_parity(o.cpu().numpy().T, want, label="int8 masked, windows")
+    plan.close()
+
+
 def test_buffer_pool_release():
     lib = _native.load()
     cx, cy, sx, sy, obs = synthetic.synthetic_case(300, 300, 64, 130)
