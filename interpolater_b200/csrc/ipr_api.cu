@@ -290,13 +290,23 @@ int ensure_weights(ipr_plan* p, int mode, const WeightParams& wp, int tile0, int
 
 // Lazily sizes the A-operand cache: the whole grid if it fits in half of the free device memory
 // (IPR_WCACHE_MB overrides), otherwise the largest chunk of cell tiles that does.
-int ensure_wcache(ipr_plan* p, char* err, size_t errlen) {
-    if (p->d_wfrag) return IPR_OK;
+int ensure_wcache(ipr_plan* p, bool need_wq, char* err, size_t errlen) {
+    if (p->d_wfrag) {
+        // digit planes wanted later than the weights (NA data arrived after an NA-free run): same chunk
+        // size; if they do not fit, this plan keeps both GEMMs on the FP64 pipe
+        if (need_wq && !p->d_wq &&
+            dev_malloc(&p->d_wq, sizeof(uint4) * (size_t)p->w_chunk_tiles * p->n_kblocks * kQTileKbU4) != cudaSuccess) {
+            cudaGetLastError();
+            p->d_wq = nullptr;
+            p->int8_mask = false;
+        }
+        return IPR_OK;
+    }
     const long long total_tiles = p->c_pad / kCellsPerCta;
     const size_t tile_bytes = (size_t)p->n_stages * kWStageDoubles * sizeof(double);
     size_t free_b = 0, total_b = 0;
     IPR_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = free_b / (p->int8_mask ? 3 : 2);   // the digit planes take as much again as the weights
+    size_t budget = free_b / (need_wq ? 3 : 2);   // the digit planes take as much again as the weights
     if (const char* e = getenv("IPR_WCACHE_MB")) budget = (size_t)atoll(e) << 20;
     long long tiles = std::min<long long>(total_tiles, (long long)(budget / tile_bytes));
     if (tiles < 1) {
@@ -307,7 +317,7 @@ int ensure_wcache(ipr_plan* p, char* err, size_t errlen) {
     IPR_CUDA(dev_malloc(&p->d_stage_list, sizeof(int) * (size_t)tiles * p->n_stages));
     IPR_CUDA(dev_malloc(&p->d_n_active, sizeof(int) * (size_t)tiles));
     p->w_chunk_tiles = (int)tiles;
-    if (p->int8_mask)
+    if (need_wq)
         IPR_CUDA(dev_malloc(&p->d_wq, sizeof(uint4) * (size_t)tiles * p->n_kblocks * kQTileKbU4));
     return IPR_OK;
 }
@@ -444,10 +454,11 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
 // One weight function over the date range: loops over cell-tile chunks of the A-operand cache
 int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int t0, int t1, double* d_out,
                     long long ld_out, char* err, size_t errlen) {
-    int rc = ensure_wcache(p, err, errlen);
-    if (rc) return rc;
     TileSets ts;
     build_tiles(p, t0, t1, idw, ts);
+    const bool masked_here = idw && (!ts.m[4].empty() || !ts.m[2].empty());
+    int rc = ensure_wcache(p, masked_here && p->int8_mask, err, errlen);
+    if (rc) return rc;
     const int total_tiles = (int)(p->c_pad / kCellsPerCta);
     for (int tile0 = 0; tile0 < total_tiles; tile0 += p->w_chunk_tiles) {
         const int n_tiles = std::min(p->w_chunk_tiles, total_tiles - tile0);
@@ -470,7 +481,7 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
         a.t_lo = t0;
         a.t_hi = t1;
         // masked granules through the error-free int8 mask contraction (opt-in)
-        const bool use_int8 = idw && p->int8_mask && (!ts.m[4].empty() || !ts.m[2].empty());
+        const bool use_int8 = masked_here && p->int8_mask && p->d_wq != nullptr;
         if (use_int8) {
             if ((rc = run_int8_masked(p, mode, wp, a, ts, t0, t1, err, errlen))) return rc;
             ts.m[4].clear();
