@@ -758,7 +758,8 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     PLAN_CUDA(dev_malloc(&p->d_wsum, sizeof(double) * p->c_pad));
     PLAN_CUDA(dev_malloc(&p->d_wmax, sizeof(double) * p->c_pad));
     p->n_kblocks = (int)round_up((p->s_pad + kQKb - 1) / kQKb, kM8Kbs);   // padded: whole pipeline stages
-    p->int8_mask = !(getenv("IPR_MASK_INT8") && atoi(getenv("IPR_MASK_INT8")) == 0);   // default on
+    // default on; the error bound of the digit planes is derived for at most 2^16 stations
+    p->int8_mask = !(getenv("IPR_MASK_INT8") && atoi(getenv("IPR_MASK_INT8")) == 0) && n_st <= 65536;
     if (p->int8_mask) {
         PLAN_CUDA(dev_malloc(&p->d_mask8, (size_t)p->n_gran * p->n_kblocks * kM8BlkBytes));
         PLAN_CUDA(dev_malloc(&p->d_fb_list, sizeof(int2) * (size_t)p->fb_cap));

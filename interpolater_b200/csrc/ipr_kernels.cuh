@@ -660,18 +660,19 @@ __global__ void idw_sparse_na_fix_kernel(const double2* __restrict__ cell_xy, co
 // kQSlices 8-bit digits below a per-cell power-of-two scale, w = 2^e_c * sum_i d_i 256^-(i+1), each
 // digit plane is contracted with the mask on the INTEGER tensor pipe (mma.sync m16n8k32 u8 x u8 ->
 // s32: the sums, at most 2000*255, are exact) and the planes are recombined in FP64.  The integer
-// pipe runs 31x faster than the FP64 one on B200 (profiles/r01_fp64_probe.log), so the eight plane
-// GEMMs cost a fraction of the FP64 GEMM they replace.  Truncation below 2^(e_c-64) bounds the error
-// by S * 2^-64 of the scale; (cell, date) pairs whose denominator is so small against the scale
-// that this exceeds 1e-9 of it (the cell's heaviest stations all missing) are listed and recomputed
-// directly by idw_direct_fix_kernel.
+// pipe runs 31x faster than the FP64 one on B200 (profiles/r01_fp64_probe.log), so the seven plane
+// GEMMs cost a fraction of the FP64 GEMM they replace.  Truncation below 2^(e_c-56) bounds the error
+// by S * 2^-56 of the scale; (cell, date) pairs whose denominator is so small against the scale
+// (< 2^-10: the cell's dominant station is missing) that this could exceed 1e-9 of it are listed and
+// recomputed directly by idw_direct_fix_kernel.
 // ---------------------------------------------------------------------------------------------
-constexpr int kQSlices = 8;
+constexpr int kQSlices = 7;
 constexpr int kQKb = 32;                                   // stations per integer k-block
 constexpr int kQTileKbU4 = kQSlices * 4 * 32;              // uint4 per (64-cell tile, k-block)
 constexpr int kM8BlkBytes = 16 * 32 * 8;                   // mask bytes per (granule, k-block), B-fragment order
 constexpr int kM8Kbs = 4;                                  // k-blocks per pipeline stage (one 16 KB bulk copy)
 constexpr int kM8Stages = 3;
+constexpr double kQDirectBelow = 0x1p-10;                  // denominators below this share of the scale are re-evaluated in FP64
 
 struct DenomArgs {
     const uint4* wq;           // [n_cell_tiles][kQSlices][n_kblocks][4 m-frags][32 lanes]
@@ -885,8 +886,9 @@ __global__ void __launch_bounds__(kThreads, 2) denom_imma_kernel(const DenomArgs
                     if (t < args.t_lo || t >= args.t_hi) continue;
                     const double d = dacc[m][n][2 * hrow + e];
                     args.out[(long long)(t - args.t_lo) * args.ld_out + cell] = d * scale;
-                    // truncation error <= S * 2^-64 (of the scale): not below 1e-9 of d when d < 2^-22
-                    if (d < 0x1p-22 && args.date_flag[t] == 0) {
+                    // truncation error < S * 2^-56 of the scale <= 2^-40 for S <= 2^16 stations (the host
+                    // disables this path beyond): guaranteed below 1e-9 of d only while d >= 2^-10
+                    if (d < kQDirectBelow && args.date_flag[t] == 0) {
                         const int slot = atomicAdd(args.fb_count, 1);
                         if (slot < args.fb_cap) args.fb_list[slot] = make_int2((int)cell, t);
                     }
