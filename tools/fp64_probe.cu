@@ -157,6 +157,41 @@ __global__ void k_hmma_bf16(float* out, int iters, unsigned a0, unsigned b0) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// do DMMA and IMMA overlap when issued by different warps of one SM? (fused masked-IDW design)
+__global__ void k_dmma_imma(double* out, int iters_d, int iters_i, int imma_warps) {
+    const int warp = threadIdx.x >> 5;
+    if (warp < 8) {
+        double c0[16], c1[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) { c0[i] = threadIdx.x; c1[i] = i; }
+        double a = 1.0000001 + threadIdx.x * 1e-9, b = 1e-9;
+        for (int it = 0; it < iters_d; it++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) dmma884(c0[i], c1[i], a, b);
+        }
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) s += c0[i] + c1[i];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else if (warp < 8 + imma_warps) {
+        int c[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { c[i][0] = threadIdx.x; c[i][1] = i; c[i][2] = 1; c[i][3] = 2; }
+        unsigned a[4] = {3u, 4u, 5u, threadIdx.x}, b[2] = {5u, 15u};
+        for (int it = 0; it < iters_i; it++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+r"(c[i][0]), "+r"(c[i][1]), "+r"(c[i][2]), "+r"(c[i][3])
+                             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+        }
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    }
+}
+
 // reciprocal variants -------------------------------------------------------
 __device__ __forceinline__ double rcp_mufu2(double x) {  // MUFU.RCP64H seed + 2 Newton steps
     double r;
@@ -277,6 +312,18 @@ int main() {
         ms = time_ms([&] { k_hmma_bf16<8><<<blocks, threads>>>((float*)out, iters, 0x3f803f80u, 0x3f803f80u); });
         ops = 2.0 * 16 * 8 * 16 * 8 * iters * (double)blocks * threads / 32;
         printf("HMMA m16n8k16 bf16 nacc=8 warps/SM=%2d : %.3f ms  %.1f TFLOP/s\n", wps, ms, ops / ms * 1e-9);
+    }
+    // ---- DMMA (8 warps) with and without IMMA (4 warps) on the same SM
+    {
+        const int it_d = 20000;
+        // IMMA work sized to ~25 % of the DMMA time when run alone: 16 DMMA/iter * 16 cyc * 2 warps per SMSP = 512 cyc/iter;
+        // 8 IMMA/iter * 8.4 cyc * 1 warp per SMSP = 67 cyc/iter -> iters_i = 0.25 * 512 / 67 * it_d
+        const int it_i = (int)(0.25 * 512.0 / 67.0 * it_d);
+        float t_d = time_ms([&] { k_dmma_imma<<<nsm, 384>>>(out, it_d, 0, 0); });
+        float t_i = time_ms([&] { k_dmma_imma<<<nsm, 384>>>(out, 0, it_i, 4); });
+        float t_b = time_ms([&] { k_dmma_imma<<<nsm, 384>>>(out, it_d, it_i, 4); });
+        printf("DMMA+IMMA co-issue (8+4 warps/SM): DMMA alone %.3f ms, IMMA alone %.3f ms, both %.3f ms (sum %.3f)\n",
+               t_d, t_i, t_b, t_d + t_i);
     }
     // ---- reciprocal variants: accuracy and cost
     {
