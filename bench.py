@@ -459,6 +459,7 @@ def run_ours(a):
             "host_buffers": "pinned (ipr_host_alloc), caller-owned",
             "calls_per_step": n_chunks,
             "ms_per_step_min_rank0": min(step_s) * 1e3,
+            "ms_steps_rank0": [round(x * 1e3, 1) for x in step_s],
             "pcie_d2h_gbs_probe": d2h_gbs,
             "pcie_floor_ms": bytes_out / (d2h_gbs * 1e9) * 1e3 if d2h_gbs > 0 else None,
             "checksum_first_1M": checksum,
