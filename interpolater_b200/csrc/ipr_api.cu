@@ -1033,7 +1033,10 @@ void ipr_release_cached_memory(void) {
 }
 
 void ipr_plan_reset_cache(ipr_plan* p) {
-    if (p) p->w_mode = -1;
+    if (p) {
+        p->w_mode = -1;
+        p->wq_mode = -1;
+    }
 }
 
 int ipr_plan_sync(ipr_plan* p) {
