@@ -423,30 +423,16 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
     if (!gran[4].empty() && (rc = launch_contract_denom<4>(p, a, gran[4], err, errlen))) return rc;
     if (!gran[2].empty() && (rc = launch_contract_denom<2>(p, a, gran[2], err, errlen))) return rc;
     {
-        const int warps = 1 << 12;  // list entries handled per launch wave; the kernel bounds itself by the count
-        const unsigned blocks = (unsigned)((p->fb_cap + 7) / 8);
-        (void)warps;
-#define IPR_DF_ARGS p->d_fb_list, p->d_fb_count, p->fb_cap, p->d_cell, p->d_st, p->n_st, p->d_perm, p->d_obs, \
-                    (long long)p->n_dates, wp, t0, a.out, a.ld_out
-        // launched over a modest grid and looped: the list is almost always empty
-        int n_fb = 0;
-        IPR_CUDA(cudaMemcpyAsync(&n_fb, p->d_fb_count, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-        IPR_CUDA(cudaStreamSynchronize(p->stream));
-        if (n_fb > p->fb_cap) {
-            set_err(err, errlen, "%d ill-scaled (cell, date) pairs exceed the int8 mask path's list (%d); "
-                    "set IPR_MASK_INT8=0", n_fb, p->fb_cap);
-            return IPR_EUNSUPPORTED;
-        }
-        if (n_fb > 0) {
-            const unsigned nb = (unsigned)((n_fb + 7) / 8);
-            (void)blocks;
-            if (mode == kIdwP2) idw_direct_fix_kernel<kIdwP2><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
-            else if (mode == kIdwEvenP) idw_direct_fix_kernel<kIdwEvenP><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
-            else idw_direct_fix_kernel<kIdwGenericP><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
-            IPR_CUDA(cudaGetLastError());
-            p->launches++;
-        }
+        // direct FP64 re-evaluation of the listed pairs; launched unconditionally (no host wait)
+#define IPR_DF_ARGS p->d_fb_list, p->d_fb_count, p->fb_cap, p->d_fb_count + 1, p->d_cell, p->d_st, p->n_st, p->d_perm, \
+                    p->d_obs, (long long)p->n_dates, wp, t0, a.out, a.ld_out
+        const unsigned nb = 296;
+        if (mode == kIdwP2) idw_direct_fix_kernel<kIdwP2><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
+        else if (mode == kIdwEvenP) idw_direct_fix_kernel<kIdwEvenP><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
+        else idw_direct_fix_kernel<kIdwGenericP><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
 #undef IPR_DF_ARGS
+        IPR_CUDA(cudaGetLastError());
+        p->launches++;
     }
     return IPR_OK;
 }
@@ -763,7 +749,8 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     if (p->int8_mask) {
         PLAN_CUDA(dev_malloc(&p->d_mask8, (size_t)p->n_gran * p->n_kblocks * kM8BlkBytes));
         PLAN_CUDA(dev_malloc(&p->d_fb_list, sizeof(int2) * (size_t)p->fb_cap));
-        PLAN_CUDA(dev_malloc(&p->d_fb_count, sizeof(int)));
+        PLAN_CUDA(dev_malloc(&p->d_fb_count, sizeof(int) * 2));   // [0] list length, [1] sticky overflow flag
+        PLAN_CUDA(cudaMemsetAsync(p->d_fb_count, 0, sizeof(int) * 2, p->stream));
     }
     PLAN_CUDA(dev_malloc(&p->d_perm, sizeof(int) * n_st));
     PLAN_CUDA(dev_malloc(&p->d_run_perm, sizeof(int) * (size_t)(p->c_pad / 8)));
@@ -1042,7 +1029,14 @@ void ipr_plan_reset_cache(ipr_plan* p) {
 int ipr_plan_sync(ipr_plan* p) {
     if (!p) return IPR_EINVAL;
     cudaSetDevice(p->device);
-    return cudaStreamSynchronize(p->stream) == cudaSuccess ? IPR_OK : IPR_ECUDA;
+    if (cudaStreamSynchronize(p->stream) != cudaSuccess) return IPR_ECUDA;
+    if (p->d_fb_count) {
+        // sticky flag of the int8 mask path: more ill-scaled (cell, date) pairs than its list holds
+        int ovf = 0;
+        if (cudaMemcpy(&ovf, p->d_fb_count + 1, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return IPR_ECUDA;
+        if (ovf) return IPR_EUNSUPPORTED;
+    }
+    return IPR_OK;
 }
 int ipr_plan_timer_start(ipr_plan* p) {
     if (!p) return IPR_EINVAL;
@@ -1317,7 +1311,12 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
         IPR_CUDA(cudaEventRecord(g.done[slot], g.copy));
     }
     tr.mark("all chunks submitted");
-    IPR_CUDA(cudaStreamSynchronize(plan->stream));
+    if ((rc = ipr_plan_sync(plan))) {
+        set_err(err, errlen, rc == IPR_EUNSUPPORTED
+                                 ? "too many ill-scaled (cell, date) pairs for the int8 mask path; set IPR_MASK_INT8=0"
+                                 : "stream synchronisation failed");
+        return rc;
+    }
     tr.mark("compute stream drained");
     IPR_CUDA(cudaStreamSynchronize(g.copy));
     tr.mark("copy stream drained");

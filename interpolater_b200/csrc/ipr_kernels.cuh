@@ -901,14 +901,18 @@ constexpr int kDenomSmemBytes = kM8Stages * (kM8Kbs * kM8BlkBytes + kM8Kbs * 4 *
 // direct FP64 evaluation of listed (cell, date) pairs: one warp each
 template <int WMODE>
 __global__ void idw_direct_fix_kernel(const int2* __restrict__ list, const int* __restrict__ count, int cap,
+                                      int* __restrict__ overflow,
                                       const double2* __restrict__ cell_xy, const double2* __restrict__ st_xy,
                                       int n_st, const int* __restrict__ perm, const double* __restrict__ obs,
                                       long long ld_obs, WeightParams wp, int t_lo, double* __restrict__ out,
                                       long long ld_out) {
+    // grid-stride over the list (usually empty: the launch is unconditional so that the host never
+    // has to wait for the count); a list that overflowed raises the sticky flag instead
+    if (*count > cap && threadIdx.x == 0 && blockIdx.x == 0) *overflow = 1;
     const int n = min(*count, cap);
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= n) return;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += n_warps) {
     const int2 it = list[w];
     const double2 c = cell_xy[it.x];
     double num = 0.0, den = 0.0;
@@ -930,6 +934,7 @@ __global__ void idw_direct_fix_kernel(const int2* __restrict__ list, const int* 
         double v = num / den;
         if (!isfinite(v) || den == 0.0) v = __longlong_as_double((long long)kNaRealBits);
         out[(long long)(it.y - t_lo) * ld_out + it.x] = v;
+    }
     }
 }
 
