@@ -80,6 +80,41 @@ size_t pool_limit_bytes() {
     return v;
 }
 
+// streams are recycled per device as well (creation / destruction occasionally takes tens of ms on a
+// shared host); a stream is only returned after it has been synchronised
+struct StreamCache {
+    std::mutex mu;
+    std::multimap<int, cudaStream_t> idle;
+};
+StreamCache& stream_cache() {
+    static StreamCache c;
+    return c;
+}
+cudaError_t acquire_stream(cudaStream_t* out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        StreamCache& C = stream_cache();
+        std::lock_guard<std::mutex> lk(C.mu);
+        auto it = C.idle.find(dev);
+        if (it != C.idle.end()) {
+            *out = it->second;
+            C.idle.erase(it);
+            return cudaSuccess;
+        }
+    }
+    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+}
+void release_stream(cudaStream_t s) {
+    if (!s) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    StreamCache& C = stream_cache();
+    std::lock_guard<std::mutex> lk(C.mu);
+    if (C.idle.count(dev) < 16) C.idle.insert({dev, s});
+    else cudaStreamDestroy(s);
+}
+
 cudaError_t dev_malloc_raw(void** out, size_t bytes) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -724,7 +759,7 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
             IPR_CUDA(e2_);                \
         }                                 \
     } while (0)
-    PLAN_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    PLAN_CUDA(acquire_stream(&p->stream));
     PLAN_CUDA(cudaEventCreate(&p->ev0));
     PLAN_CUDA(cudaEventCreate(&p->ev1));
     PLAN_CUDA(dev_malloc(&p->d_cell, sizeof(double2) * p->c_pad));
@@ -866,7 +901,7 @@ void ipr_plan_destroy(ipr_plan* p) {
     dev_free(p->d_active_total);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
-    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->stream) release_stream(p->stream);   // synchronised above
     delete p;
 }
 
@@ -1245,7 +1280,7 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
             cudaSetDevice(p->device);
             if (copy) {
                 cudaStreamSynchronize(copy);
-                cudaStreamDestroy(copy);
+                release_stream(copy);   // synchronised just above
             }
             for (int i = 0; i < kRing; i++) {
                 dev_free(ring[i]);
@@ -1274,7 +1309,7 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
     for (int s = 0; s < n_stacks; s++)
         for (int t = 0; t < nd; t += chunk) items.push_back({s, t, std::min(nd, t + chunk)});
     const size_t slot_doubles = (size_t)job.n_cells * std::min(chunk, (int)round_up(nd, 16));
-    IPR_CUDA(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+    IPR_CUDA(acquire_stream(&g.copy));
     PageableSink sink;
     if (!job.out_pinned && (rc = sink.start())) {
         set_err(err, errlen, "could not set up the pinned staging ring for a pageable output buffer");

@@ -15,8 +15,5 @@ plan.close()
 hp = lib.ipr_host_alloc(Cn * D * 8)
 out = np.ctypeslib.as_array((C.c_double * (Cn * D)).from_address(hp)).reshape(D, Cn).T
 obs_f = np.asfortranarray(obs)
-for i in range(3):
-    t = time.perf_counter(); engine.idw_grid(cx, cy, sx, sy, obs_f, out=out, devices=[0]); print("idw_grid e2e", time.perf_counter() - t)
-out2 = np.empty((Cn, D), dtype=np.float64, order="F")   # pageable, untouched
-for i in range(2):
-    t = time.perf_counter(); engine.idw_grid(cx, cy, sx, sy, obs_f, out=out2, devices=[0]); print("idw_grid e2e PAGEABLE out", time.perf_counter() - t)
+for i in range(12):
+    t = time.perf_counter(); engine.idw_grid(cx, cy, sx, sy, obs_f, out=out, devices=[0]); print("idw_grid e2e", time.perf_counter() - t, flush=True)
