@@ -44,8 +44,8 @@ def parse_args():
     ap.add_argument("--stations", type=int, default=2000)
     ap.add_argument("--dates", type=int, default=3650)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: every GPU owns its own --dates-day block (default, no tile straddles GPUs); "
-                         "strong: the --dates days are split over the GPUs on 128-date granules")
+                    help="weak: every GPU owns its own --dates-day block of the record (default); "
+                         "strong: ONE job, the cells are split over the GPUs on 64-cell tiles")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-cells", type=int, default=10000)
@@ -278,15 +278,16 @@ def run_ours(a):
         return float(t.item())
 
     cx, cy, sx, sy, obs = make_inputs(a, rank if a.scaling == "weak" else 0)
-    total_dates = obs.shape[0] * world
+    total_cells = cx.shape[0]
+    total_dates = obs.shape[0] * (world if a.scaling == "weak" else 1)
     if a.scaling == "strong":
+        # one job over all GPUs: contiguous cell ranges (nothing computed twice, equal shares)
         from interpolater_b200 import sharding
 
-        b = sharding.date_block_bounds(obs.shape[0], world)
-        obs = np.ascontiguousarray(obs[b[rank]:b[rank + 1]])
-        total_dates = b[-1]
-        if obs.shape[0] == 0:
-            raise SystemExit("strong scaling: fewer 128-date granules than GPUs")
+        b = sharding.cell_block_bounds(total_cells, world)
+        cx, cy = np.ascontiguousarray(cx[b[rank]:b[rank + 1]]), np.ascontiguousarray(cy[b[rank]:b[rank + 1]])
+        if cx.shape[0] == 0:
+            raise SystemExit("strong scaling: fewer 64-cell tiles than GPUs")
     C, S, D = cx.shape[0], sx.shape[0], obs.shape[0]
     n_stacks = len(RADII_M) if a.workload == "cressman" else 1
     radii = np.asarray(RADII_M)
@@ -322,7 +323,7 @@ def run_ours(a):
     clocks = sampler.stop()
     launches = plan.launch_count - l0
     ms_step = max_over_ranks(ms_total / a.steps)
-    value = C * total_dates / (ms_step * 1e-3)
+    value = total_cells * total_dates / (ms_step * 1e-3)
 
     # dominant kernel: the DMMA contraction.  Its launches are timed alone here (same stream, CUDA
     # events; obs preparation excluded, weights cached — for the multi-radius Cressman the cache
@@ -450,7 +451,7 @@ def run_ours(a):
         sec = max_over_ranks(sec)
         checksum = float(np.nansum(host_out[: min(host_out.size, 1 << 20)]))
         e2e = {
-            "value": C * total_dates / sec,
+            "value": total_cells * total_dates / sec,
             "unit": UNIT,
             "h2d_bytes_per_step": int((2 * C + 2 * S + S * D) * 8),
             "d2h_bytes_per_step": int(bytes_out),
@@ -488,11 +489,11 @@ def run_ours(a):
             "data": "synthetic",
             "config": {
                 "workload": workload_name(a),
-                "n_cells": C, "n_stations": S, "n_dates_total": int(total_dates), "n_dates_rank0": D,
-                "n_stacks": n_stacks,
+                "n_cells": int(total_cells), "n_cells_rank0": C, "n_stations": S, "n_dates_total": int(total_dates),
+                "n_dates_rank0": D, "n_stacks": n_stacks,
                 "sharding": ("one independent %d-day date block per GPU" % D if a.scaling == "weak" else
-                             "%d days split over %d GPUs on 128-date granules" % (total_dates, world))
-                            + ", no data-path collective",
+                             "%d cells split over %d GPUs on 64-cell tiles, every GPU all %d days"
+                             % (total_cells, world, D)) + ", no data-path collective",
                 "l2": "outputs (%.1f GB/step) >> 126 MB L2: every step streams through and flushes L2"
                       % (n_stacks * C * D * 8e-9),
             },

@@ -48,8 +48,10 @@ double ipr_na_real(void);
  *   st_x, st_y       n_st         training-station coordinates, aligned with obs columns
  *   obs              n_dates x n_st, column-major (each station's series contiguous, as the
  *                    columns of BD_Obs are); NaN/NA = missing
- *   devices          n_devices CUDA ordinals (NULL / 0 => device 0); date blocks are sharded
- *                    contiguously over them, no inter-GPU reduction
+ *   devices          n_devices CUDA ordinals (NULL / 0 => device 0); the cells are split into
+ *                    contiguous ranges (64-cell tiles) over them, every device computing all dates
+ *                    of its cells and writing its own columns of every layer: nothing is computed
+ *                    twice and there is no inter-GPU exchange
  *   out              caller-owned, column-major n_cells x n_dates (one layer per date); page-locked
  *                    memory receives the D2H copies directly, pageable memory (an R vector) is
  *                    filled through a pinned staging ring with a multi-threaded first touch

@@ -1092,10 +1092,10 @@ void* ipr_plan_stream(const ipr_plan* p) { return p ? (void*)p->stream : nullptr
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
-// One-shot host-buffer entry points: multi-GPU date-block scheduler.
-// Each device gets a contiguous date block [d0, d1) (no inter-GPU reduction); inside a
-// device the block is processed in chunks through a ring of device buffers so that the D2H copy of
-// chunk i overlaps the kernels of chunk i+1.
+// One-shot host-buffer entry points: multi-GPU scheduler.
+// Each device gets a contiguous range of cells [c0, c1) on 64-cell tile boundaries (no inter-GPU
+// exchange); inside a device the dates are processed in 128-date chunks through a ring
+// of device buffers so that the D2H copy of chunk i overlaps the kernels of chunk i+1.
 // ---------------------------------------------------------------------------------------------
 namespace {
 
@@ -1151,8 +1151,29 @@ public:
         return IPR_OK;
     }
 
-    // enqueue device -> host copy of `bytes` from d_src to pageable dst, on `stream`
-    int push(const char* d_src, char* dst, size_t bytes, cudaStream_t stream) {
+    // enqueue device -> host copy of `rows` rows of `width` bytes (contiguous on the device) to pageable
+    // memory with row pitch `pitch`, on `stream`
+    int push2d(const char* d_src, char* dst, size_t width, size_t rows, size_t pitch, cudaStream_t stream) {
+        if (width == pitch || rows == 1) return push(d_src, dst, width * rows, 0, 0, stream);
+        if (width > kSlotBytes) {  // a single row larger than a staging slot: row by row
+            for (size_t r = 0; r < rows; r++) {
+                const int rc = push(d_src + r * width, dst + r * pitch, width, 0, 0, stream);
+                if (rc) return rc;
+            }
+            return IPR_OK;
+        }
+        const size_t rows_per = kSlotBytes / width;
+        for (size_t r0 = 0; r0 < rows; r0 += rows_per) {
+            const size_t nr = std::min(rows_per, rows - r0);
+            const int rc = push(d_src + r0 * width, dst + r0 * pitch, width * nr, width, pitch, stream);
+            if (rc) return rc;
+        }
+        return IPR_OK;
+    }
+
+    // `bytes` contiguous on the device; on the host either contiguous (width == 0) or rows of `width`
+    // bytes at `pitch` (then bytes is a multiple of width and fits one slot)
+    int push(const char* d_src, char* dst, size_t bytes, size_t width, size_t pitch, cudaStream_t stream) {
         for (size_t off = 0; off < bytes; off += kSlotBytes) {
             const size_t n = std::min(kSlotBytes, bytes - off);
             const long long id = issued_;
@@ -1167,7 +1188,7 @@ public:
                 return IPR_ECUDA;
             {
                 std::lock_guard<std::mutex> lk(mu_);
-                work_.push_back({dst + off, n});
+                work_.push_back({dst + off, n, width, pitch});
                 issued_++;
             }
             cv_.notify_all();
@@ -1194,7 +1215,7 @@ public:
     }
 
 private:
-    struct Work { char* dst; size_t bytes; };
+    struct Work { char* dst; size_t bytes, width, pitch; };
     static std::mutex& pinned_mu() { static std::mutex m; return m; }
     static std::vector<void*>& pinned_free() { static std::vector<void*> v; return v; }
     void release_slots() {
@@ -1224,11 +1245,23 @@ private:
             }
             // parallel first-touch + copy
             const char* src = static_cast<const char*>(slot_[k]);
-            const size_t per = (w.bytes / n_threads_ + 4095) & ~size_t(4095);
             std::vector<std::thread> th;
-            for (unsigned t = 0; t < n_threads_; t++) {
-                const size_t lo = std::min(w.bytes, (size_t)t * per), hi = std::min(w.bytes, lo + per);
-                if (hi > lo) th.emplace_back([=] { memcpy(w.dst + lo, src + lo, hi - lo); });
+            if (w.width == 0) {
+                const size_t per = (w.bytes / n_threads_ + 4095) & ~size_t(4095);
+                for (unsigned t = 0; t < n_threads_; t++) {
+                    const size_t lo = std::min(w.bytes, (size_t)t * per), hi = std::min(w.bytes, lo + per);
+                    if (hi > lo) th.emplace_back([=] { memcpy(w.dst + lo, src + lo, hi - lo); });
+                }
+            } else {
+                const size_t rows = w.bytes / w.width;
+                const size_t per = (rows + n_threads_ - 1) / n_threads_;
+                for (unsigned t = 0; t < n_threads_; t++) {
+                    const size_t lo = std::min(rows, (size_t)t * per), hi = std::min(rows, lo + per);
+                    if (hi > lo)
+                        th.emplace_back([=] {
+                            for (size_t r = lo; r < hi; r++) memcpy(w.dst + r * w.pitch, src + r * w.width, w.width);
+                        });
+                }
             }
             for (auto& x : th) x.join();
             {
@@ -1262,12 +1295,14 @@ struct Trace {
     }
 };
 
-int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, size_t errlen) {
-    if (d0 >= d1) return IPR_OK;
+// One device's share of a host-buffer job: cells [c0, c1) for every date (and every stack).
+int run_device_block(const HostJob& job, int device, long long c0, long long c1, char* err, size_t errlen) {
+    if (c0 >= c1) return IPR_OK;
     Trace tr;
-    const int nd = d1 - d0;
+    const int nd = job.n_dates;
+    const long long nc = c1 - c0;
     ipr_plan* plan = nullptr;
-    int rc = ipr_plan_create(&plan, device, job.cell_x, job.cell_y, job.n_cells, job.st_x, job.st_y, job.n_st, nd, err,
+    int rc = ipr_plan_create(&plan, device, job.cell_x + c0, job.cell_y + c0, nc, job.st_x, job.st_y, job.n_st, nd, err,
                              errlen);
     if (rc) return rc;
     struct Guard {
@@ -1293,10 +1328,11 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
         }
     } g{plan};
     if ((job.round_mode != 0 || job.cell_keep) &&
-        (rc = ipr_plan_set_post(plan, job.round_mode, job.n_round, job.cell_keep, err, errlen)))
+        (rc = ipr_plan_set_post(plan, job.round_mode, job.n_round, job.cell_keep ? job.cell_keep + c0 : nullptr, err,
+                                errlen)))
         return rc;
     tr.mark("plan created (allocations, coordinate upload, zero-distance scan)");
-    rc = plan_set_obs_ld(plan, job.obs + d0, job.n_dates, err, errlen);
+    rc = plan_set_obs_ld(plan, job.obs, job.n_dates, err, errlen);
     if (rc) return rc;
     tr.mark("obs uploaded and prepared");
     const int n_stacks = job.cressman ? job.n_radii : 1;
@@ -1308,7 +1344,7 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
     std::vector<Item> items;
     for (int s = 0; s < n_stacks; s++)
         for (int t = 0; t < nd; t += chunk) items.push_back({s, t, std::min(nd, t + chunk)});
-    const size_t slot_doubles = (size_t)job.n_cells * std::min(chunk, (int)round_up(nd, 16));
+    const size_t slot_doubles = (size_t)nc * std::min(chunk, (int)round_up(nd, 16));
     IPR_CUDA(acquire_stream(&g.copy));
     PageableSink sink;
     if (!job.out_pinned && (rc = sink.start())) {
@@ -1327,19 +1363,23 @@ int run_device_block(const HostJob& job, int device, int d0, int d1, char* err, 
         const int slot = (int)(ii % n_ring);
         if ((int)ii >= n_ring) IPR_CUDA(cudaStreamWaitEvent(plan->stream, g.done[slot], 0));
         if (job.cressman)
-            rc = ipr_plan_cressman(plan, job.radii + it.stack, 1, it.t0, it.t1, g.ring[slot], job.n_cells, 0, err,
-                                   errlen);
+            rc = ipr_plan_cressman(plan, job.radii + it.stack, 1, it.t0, it.t1, g.ring[slot], nc, 0, err, errlen);
         else
-            rc = ipr_plan_idw(plan, job.p, it.t0, it.t1, g.ring[slot], job.n_cells, err, errlen);
+            rc = ipr_plan_idw(plan, job.p, it.t0, it.t1, g.ring[slot], nc, err, errlen);
         if (rc) return rc;
         IPR_CUDA(cudaEventRecord(g.computed[slot], plan->stream));
         IPR_CUDA(cudaStreamWaitEvent(g.copy, g.computed[slot], 0));
-        double* dst = job.out + (size_t)it.stack * job.n_cells * job.n_dates + (size_t)(d0 + it.t0) * job.n_cells;
-        const size_t bytes = sizeof(double) * (size_t)job.n_cells * (it.t1 - it.t0);
+        // layer t of the caller's matrix is a row of n_cells doubles; this device owns columns [c0, c1)
+        double* dst = job.out + (size_t)it.stack * job.n_cells * job.n_dates + (size_t)it.t0 * job.n_cells + c0;
+        const size_t width = sizeof(double) * (size_t)nc, pitch = sizeof(double) * (size_t)job.n_cells;
+        const size_t rows = (size_t)(it.t1 - it.t0);
         if (job.out_pinned) {
-            IPR_CUDA(cudaMemcpyAsync(dst, g.ring[slot], bytes, cudaMemcpyDeviceToHost, g.copy));
-        } else if ((rc = sink.push(reinterpret_cast<const char*>(g.ring[slot]), reinterpret_cast<char*>(dst), bytes,
-                                   g.copy))) {
+            if (width == pitch)
+                IPR_CUDA(cudaMemcpyAsync(dst, g.ring[slot], width * rows, cudaMemcpyDeviceToHost, g.copy));
+            else
+                IPR_CUDA(cudaMemcpy2DAsync(dst, pitch, g.ring[slot], width, width, rows, cudaMemcpyDeviceToHost, g.copy));
+        } else if ((rc = sink.push2d(reinterpret_cast<const char*>(g.ring[slot]), reinterpret_cast<char*>(dst), width,
+                                     rows, pitch, g.copy))) {
             set_err(err, errlen, "staged device-to-host copy failed");
             return rc;
         }
@@ -1385,14 +1425,15 @@ int run_host_job(const HostJob& job, const int* devices, int n_devices, char* er
         if (e != cudaSuccess) cudaGetLastError();
         jobx.out_pinned = (e == cudaSuccess && attr.type == cudaMemoryTypeHost);
     }
-    // contiguous date blocks, as even as possible in units of 32 dates (the width step of the
-    // contraction's tail tiles); every device numbers its own dates from 0, so no other alignment
-    // is needed
-    std::vector<int> bounds(G + 1, 0);
+    // Every output element depends only on its own cell and date, so the devices split the
+    // CELLS into contiguous ranges on 64-cell tile boundaries: nothing is computed twice (a date split
+    // would make every device regenerate all cell x station weights), the shares are equal to within
+    // one tile, and each device writes its own column range of every layer.  No inter-GPU exchange.
+    std::vector<long long> bounds(G + 1, 0);
     {
-        const int n_blk = (job.n_dates + 31) / 32;
-        for (int g = 0; g <= G; g++) bounds[g] = (int)std::min<long long>(job.n_dates, (long long)n_blk * g / G * 32);
-        bounds[G] = job.n_dates;
+        const long long n_tiles = (job.n_cells + kCellsPerCta - 1) / kCellsPerCta;
+        for (int g = 0; g <= G; g++) bounds[g] = std::min<long long>(job.n_cells, n_tiles * g / G * kCellsPerCta);
+        bounds[G] = job.n_cells;
     }
     std::vector<int> rcs(G, IPR_OK);
     std::vector<std::string> errs(G, std::string(256, '\0'));

@@ -452,17 +452,18 @@ def test_weight_cache_chunking_and_reset(monkeypatch):
 
 
 @pytest.mark.parametrize("n_dates", [300, 70, 20])
-def test_date_block_scheduler_on_one_gpu(n_dates):
-    """The multi-GPU date-block scheduler of the host-buffer entry points, exercised on a single
-    device by listing it several times (one host thread + plan per entry): the shards' results must
-    tile the caller's matrix exactly like a single-device run, for IDW and for every Cressman stack."""
+def test_multi_device_scheduler_on_one_gpu(n_dates):
+    """The multi-GPU scheduler of the host-buffer entry points (contiguous cell ranges per device,
+    2-D copies into the caller's matrix), exercised on a single device by listing it several times
+    (one host thread + plan per entry): the shards must tile the matrix exactly like a single-device
+    run, for IDW and for every Cressman stack, into pageable (staged) memory."""
     cx, cy, sx, sy, obs = synthetic.synthetic_case(25, 20, 45, n_dates, na_frac=0.04, plant_zero_dist=1,
                                                    all_na_dates=(3,), seed=n_dates)
     one = engine.idw_grid(cx, cy, sx, sy, obs, devices=[0])
     for devs in ([0, 0], [0, 0, 0, 0, 0]):
         many = engine.idw_grid(cx, cy, sx, sy, obs, devices=devs)
-        # not bit-identical: each shard numbers its dates from 0, so a date can fall in a granule that
-        # takes the other NA path (masked GEMM vs corrected denominator) than in the single-device run
+        # cell tiles start elsewhere in each shard, which changes nothing per cell except the order in
+        # which a thread block sums: identical to rounding
         assert_parity(many, one, tol=1e-12, label=f"devices={devs}")
     radii = np.array([4e3, 9e3, 30e3])
     c1 = np.ascontiguousarray(engine.cressman_grid(cx, cy, sx, sy, obs, radii, devices=[0]))

@@ -209,6 +209,15 @@ def test_cressman_error_strings(packaged):
 
 
 # ----------------------------------------------------------------------------- sharding
+def test_cell_block_bounds():
+    for n, g in [(1_000_000, 8), (24, 8), (64, 2), (65, 2), (1, 4), (1000, 3)]:
+        b = sharding.cell_block_bounds(n, g)
+        assert b[0] == 0 and b[-1] == n and len(b) == g + 1
+        assert all(b[i] <= b[i + 1] for i in range(g)) and all(x % 64 == 0 for x in b[:-1])
+    b = sharding.cell_block_bounds(1_000_000, 8)
+    assert max(b[i + 1] - b[i] for i in range(8)) - min(b[i + 1] - b[i] for i in range(8)) <= 64
+
+
 def test_date_block_bounds():
     for n, g in [(3650, 8), (3650, 1), (60, 8), (128, 2), (129, 2), (1, 4), (1000, 3)]:
         b = sharding.date_block_bounds(n, g)
