@@ -659,9 +659,9 @@ __global__ void idw_sparse_na_fix_kernel(const double2* __restrict__ cell_xy, co
 // is the second GEMM of the masked path.  m is exact in 8 bits, so the weights are cut into
 // kQSlices 8-bit digits below a per-cell power-of-two scale, w = 2^e_c * sum_i d_i 256^-(i+1), each
 // digit plane is contracted with the mask on the INTEGER tensor pipe (mma.sync m16n8k32 u8 x u8 ->
-// s32: the sums, at most 2000*255, are exact) and the planes are recombined in FP64.  The integer
-// pipe runs 31x faster than the FP64 one on B200 (profiles/r01_fp64_probe.log), so the seven plane
-// GEMMs cost a fraction of the FP64 GEMM they replace.  Truncation below 2^(e_c-56) bounds the error
+// s32: the sums, at most 2000*255, are exact) and the planes are recombined in FP64.  IMMA runs 31x
+// faster than DMMA on B200 (profiles/r01_fp64_probe.log; same tensor pipe, the two do not overlap), so
+// the seven plane GEMMs cost a fraction of the FP64 GEMM they replace.  Truncation below 2^(e_c-56) bounds the error
 // by S * 2^-56 of the scale; (cell, date) pairs whose denominator is so small against the scale
 // (< 2^-10: the cell's dominant station is missing) that this could exceed 1e-9 of it are listed and
 // recomputed directly by idw_direct_fix_kernel.
