@@ -227,3 +227,65 @@ def test_date_block_bounds():
     b = sharding.date_block_bounds(3650, 8)
     assert b == [0, 448, 896, 1376, 1824, 2272, 2752, 3200, 3650]
     assert max(b[i + 1] - b[i] for i in range(8)) <= 480     # balanced to within one 32-date step
+
+
+# ----------------------------------------------------------------------------- ingestion
+def _write_station_csvs(folder):
+    """Four station files shaped like the reference's inst/extdata/Folds_ejs_create_data
+    (quoted header, ISO dates, one value column), with ragged date ranges and gaps."""
+    days = pd.date_range("2014-12-28", "2015-03-05", freq="D")
+    rng = np.random.default_rng(7)
+    series = {}
+    for k, name in enumerate(["M001", "M002", "M003", "M004"]):
+        sel = days[k * 3: len(days) - k * 2]
+        vals = np.round(rng.gamma(0.8, 8.0, len(sel)) * (rng.random(len(sel)) < 0.5), 1)
+        txt = [f'"Date","{name}"']
+        for d, v in zip(sel, vals):
+            miss = name == "M003" and d.day % 5 == 0      # 20 % gaps in M003
+            txt.append(f"{d.date()},{'NA' if miss else v}")
+        (folder / f"{name}.csv").write_text("\n".join(txt) + "\n")
+        series[name] = dict(zip([str(d.date()) for d in sel], vals))
+    (folder / "notes.txt").write_text("ignored\n")
+    return series
+
+
+def test_create_data_matches_reference_expectations(tmp_path):
+    """tests/testthat/test-create_data.R:8-38 — a table without max.na, a (data, Na_stations) pair
+    with it, and the same table when the files are read in parallel."""
+    from interpolater_b200 import ingest
+    series = _write_station_csvs(tmp_path)
+    out = ingest.create_data(tmp_path, Start_date="2015-01-01", End_Date="2015-03-01", ncores=None, max_na=None)
+    assert isinstance(out, pd.DataFrame)
+    assert list(out.columns) == ["Date", "M001", "M002", "M003", "M004"]
+    assert len(out) == 60 and out["Date"].is_monotonic_increasing
+    assert str(out["Date"].iloc[0])[:10] == "2015-01-01" and str(out["Date"].iloc[-1])[:10] == "2015-03-01"
+    for name, rec in series.items():
+        for d, v in zip(out["Date"], out[name]):
+            key = str(d)[:10]
+            if name == "M003" and int(key[-2:]) % 5 == 0:
+                assert math.isnan(v)
+            elif key in rec:
+                assert v == rec[key]
+            else:
+                assert math.isnan(v)            # outside that station's record -> NA (all = TRUE)
+    par = ingest.create_data(tmp_path, Start_date="2015-01-01", End_Date="2015-03-01", ncores=2)
+    pd.testing.assert_frame_equal(out, par)
+
+    flt = ingest.create_data(tmp_path, Start_date="2015-01-01", End_Date="2015-03-01", max_na=10)
+    assert set(flt) == {"data", "Na_stations"}
+    pct = flt["Na_stations"].iloc[0]
+    assert pct["M001"] == 0.0 and pct["M003"] == pytest.approx(100.0 * 13 / 60)
+    assert "M003" not in flt["data"].columns and "M001" in flt["data"].columns
+    # strict "<": a station at exactly the threshold is dropped (R/create_data.R:89)
+    edge = ingest.create_data(tmp_path, Start_date="2015-01-01", End_Date="2015-03-01", max_na=100.0 * 13 / 60)
+    assert "M003" not in edge["data"].columns
+
+    dates, cols, z = ingest.obs_matrix(out)
+    assert z.flags.f_contiguous and z.shape == (60, 4) and cols == ["M001", "M002", "M003", "M004"]
+
+
+def test_create_data_rejects_wrong_column_count(tmp_path):
+    from interpolater_b200 import ingest
+    (tmp_path / "M009.csv").write_text("Date,a,b\n2015-01-01,1,2\n")
+    with pytest.raises(ValueError, match="2 names"):
+        ingest.create_data(tmp_path, "2015-01-01", "2015-01-31")
