@@ -1,12 +1,14 @@
 // interpolater_b200 — C ABI implementation: device-resident plan, kernel scheduling, and the
-// one-shot host-buffer entry points with the multi-GPU date-block scheduler.
+// one-shot host-buffer entry points with the multi-GPU scheduler (cell ranges per device).
 // See include/interpolater_b200.h for the contract and the reference lines each call replaces.
 #include "../../include/interpolater_b200.h"
 
 #include <algorithm>
 #include <condition_variable>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <new>
 #include <chrono>
 #include <utility>
 #include <cmath>
@@ -44,11 +46,26 @@ void set_err(char* err, size_t errlen, const char* fmt, ...) {
 
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
+// No C++ exception may cross the C ABI (the caller is R's .Call or ctypes): host allocations of the
+// staging vectors are the realistic source.
+template <class F>
+int no_throw(char* err, size_t errlen, F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        set_err(err, errlen, "out of host memory");
+        return IPR_ENOMEM;
+    } catch (const std::exception& e) {
+        set_err(err, errlen, "internal error: %s", e.what());
+        return IPR_ECUDA;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Device buffer pool.  cudaMalloc / cudaFree of the multi-GB work buffers (A-operand cache, output
 // ring, B operand) was measured to cost anything from 15 to 600 ms per host-buffer call depending
-// on the allocator's mood; freed buffers >= 1 MiB are therefore kept per device and reused by
-// exact size.  ipr_release_cached_memory() (or memory pressure) returns them to the driver.
+// on the allocator's mood; freed buffers are therefore kept per device and reused by exact size.
+// ipr_release_cached_memory() (or memory pressure) returns them to the driver.
 // ---------------------------------------------------------------------------------------------
 struct DevicePool {
     std::mutex mu;
@@ -153,7 +170,9 @@ void dev_free(void* ptr) {
     const int dev = it->second.first;
     const size_t bytes = it->second.second;
     P.live.erase(it);
-    if (bytes >= (1u << 20) && P.idle_bytes + bytes <= pool_limit_bytes()) {
+    // small buffers are kept too: a plan frees ~20 of them, and cudaFree was traced at up to 0.5 s for
+    // the lot on a busy host (it synchronises the device and unmaps), 0.2-0.5 s out of a 0.57 s call
+    if (P.idle_bytes + bytes <= pool_limit_bytes() && P.idle.size() < 4096) {
         P.idle.insert({{dev, bytes}, ptr});
         P.idle_bytes += bytes;
     } else {
@@ -250,6 +269,8 @@ struct ipr_plan {
     int* d_perm = nullptr;        // spatial (Morton) order of the stations: sorted position -> input index
     double4* d_stage_box = nullptr;  // bounding box of each station stage (Cressman culling in weights_kernel)
     int* d_run_perm = nullptr;    // Morton order of the 8-cell runs: 8 consecutive entries = one compact cell tile
+    std::vector<double2> h_run_xy;   // first cell of every run; d_run_perm is built from it on the first Cressman call
+    bool run_perm_ready = false;
     unsigned long long* d_active_total = nullptr;
     unsigned long long stage_tiles_total = 0;  // (cell tile, stage) blocks the dense product would visit
     int w_chunk_tiles = 0;   // capacity of d_wfrag in cell tiles
@@ -285,6 +306,24 @@ int launch_contract(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles,
         IPR_CUDA(cudaGetLastError());
         p->launches++;
     }
+    return IPR_OK;
+}
+
+// Cressman cell tiles: 8 Morton-consecutive runs of 8 consecutive cells, i.e. compact 2-D patches
+// instead of 64 x 1 strips, so that fewer station stages reach any cell of a tile.
+int ensure_run_perm(ipr_plan* p, char* err, size_t errlen) {
+    if (p->run_perm_ready) return IPR_OK;
+    const int n_runs = (int)p->h_run_xy.size();
+    std::vector<double> rx(n_runs), ry(n_runs);
+    for (int i = 0; i < n_runs; i++) {
+        rx[i] = p->h_run_xy[i].x;
+        ry[i] = p->h_run_xy[i].y;
+    }
+    const std::vector<int> run_perm = morton_order(rx.data(), ry.data(), n_runs);
+    IPR_CUDA(cudaMemcpyAsync(p->d_run_perm, run_perm.data(), sizeof(int) * run_perm.size(), cudaMemcpyHostToDevice,
+                             p->stream));
+    IPR_CUDA(cudaStreamSynchronize(p->stream));   // the staging vector goes out of scope
+    p->run_perm_ready = true;
     return IPR_OK;
 }
 
@@ -348,12 +387,23 @@ int ensure_wcache(ipr_plan* p, bool need_wq, char* err, size_t errlen) {
         set_err(err, errlen, "not enough device memory for the weight cache (%zu bytes per cell tile)", tile_bytes);
         return IPR_ENOMEM;
     }
-    IPR_CUDA(dev_malloc(&p->d_wfrag, tile_bytes * tiles));
-    IPR_CUDA(dev_malloc(&p->d_stage_list, sizeof(int) * (size_t)tiles * p->n_stages));
-    IPR_CUDA(dev_malloc(&p->d_n_active, sizeof(int) * (size_t)tiles));
+    cudaError_t e = dev_malloc(&p->d_wfrag, tile_bytes * tiles);
+    if (e == cudaSuccess) e = dev_malloc(&p->d_stage_list, sizeof(int) * (size_t)tiles * p->n_stages);
+    if (e == cudaSuccess) e = dev_malloc(&p->d_n_active, sizeof(int) * (size_t)tiles);
+    if (e == cudaSuccess && need_wq)
+        e = dev_malloc(&p->d_wq, sizeof(uint4) * (size_t)tiles * p->n_kblocks * kQTileKbU4);
+    if (e != cudaSuccess) {  // leave the plan without a cache, so that a later call starts over
+        dev_free(p->d_wfrag);
+        dev_free(p->d_stage_list);
+        dev_free(p->d_n_active);
+        dev_free(p->d_wq);
+        p->d_wfrag = nullptr;
+        p->d_stage_list = nullptr;
+        p->d_n_active = nullptr;
+        p->d_wq = nullptr;
+        IPR_CUDA(e);
+    }
     p->w_chunk_tiles = (int)tiles;
-    if (need_wq)
-        IPR_CUDA(dev_malloc(&p->d_wq, sizeof(uint4) * (size_t)tiles * p->n_kblocks * kQTileKbU4));
     return IPR_OK;
 }
 
@@ -480,6 +530,7 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
     const bool masked_here = idw && (!ts.m[4].empty() || !ts.m[2].empty());
     int rc = ensure_wcache(p, masked_here && p->int8_mask, err, errlen);
     if (rc) return rc;
+    if (mode == kCressman && (rc = ensure_run_perm(p, err, errlen))) return rc;
     const int total_tiles = (int)(p->c_pad / kCellsPerCta);
     for (int tile0 = 0; tile0 < total_tiles; tile0 += p->w_chunk_tiles) {
         const int n_tiles = std::min(p->w_chunk_tiles, total_tiles - tile0);
@@ -501,17 +552,14 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
         a.n_stages = p->n_stages;
         a.t_lo = t0;
         a.t_hi = t1;
-        // masked granules through the error-free int8 mask contraction (opt-in)
+        // masked granules through the error-free int8 mask contraction (every chunk of cell tiles)
         const bool use_int8 = masked_here && p->int8_mask && p->d_wq != nullptr;
-        if (use_int8) {
-            if ((rc = run_int8_masked(p, mode, wp, a, ts, t0, t1, err, errlen))) return rc;
-            ts.m[4].clear();
-            ts.m[2].clear();
-        }
+        if (use_int8 && (rc = run_int8_masked(p, mode, wp, a, ts, t0, t1, err, errlen))) return rc;
         if (!ts.u[8].empty() && (rc = launch_contract<8, false>(p, a, ts.u[8], err, errlen))) return rc;
         if (!ts.u[6].empty() && (rc = launch_contract<6, false>(p, a, ts.u[6], err, errlen))) return rc;
         if (!ts.u[4].empty() && (rc = launch_contract<4, false>(p, a, ts.u[4], err, errlen))) return rc;
         if (!ts.u[2].empty() && (rc = launch_contract<2, false>(p, a, ts.u[2], err, errlen))) return rc;
+        if (use_int8) continue;   // the masked granules of this chunk are done
         if (!ts.m[4].empty() && (rc = launch_contract<4, true>(p, a, ts.m[4], err, errlen))) return rc;
         if (!ts.m[2].empty() && (rc = launch_contract<2, true>(p, a, ts.m[2], err, errlen))) return rc;
     }
@@ -712,8 +760,9 @@ void ipr_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
-int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const double* cell_y, int64_t n_cells,
-                    const double* st_x, const double* st_y, int32_t n_st, int32_t n_dates, char* err, size_t errlen) {
+static int plan_create_impl(ipr_plan** plan, int device, const double* cell_x, const double* cell_y, int64_t n_cells,
+                            const double* st_x, const double* st_y, int32_t n_st, int32_t n_dates, char* err,
+                            size_t errlen) {
     if (!plan || !cell_x || !cell_y || !st_x || !st_y) {
         set_err(err, errlen, "NULL argument");
         return IPR_EINVAL;
@@ -740,7 +789,9 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
         return IPR_EUNSUPPORTED;
     }
     IPR_CUDA(cudaSetDevice(device));
-    ipr_plan* p = new ipr_plan();
+    // destroyed on every early return (error codes and exceptions alike)
+    std::unique_ptr<ipr_plan, void (*)(ipr_plan*)> holder(new ipr_plan(), ipr_plan_destroy);
+    ipr_plan* p = holder.get();
     p->device = device;
     p->n_cells = n_cells;
     p->c_pad = round_up(n_cells, kCellsPerCta);
@@ -751,81 +802,61 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
     p->n_stages = p->s_pad / kKT;
     p->z_doubles = (size_t)p->n_gran * p->n_stages * kBlkDoubles;
     p->pair_capacity = std::max(4 * n_st, 65536);
-#define PLAN_CUDA(call)                   \
-    do {                                  \
-        cudaError_t e2_ = (call);         \
-        if (e2_ != cudaSuccess) {         \
-            ipr_plan_destroy(p);          \
-            IPR_CUDA(e2_);                \
-        }                                 \
-    } while (0)
-    PLAN_CUDA(acquire_stream(&p->stream));
-    PLAN_CUDA(cudaEventCreate(&p->ev0));
-    PLAN_CUDA(cudaEventCreate(&p->ev1));
-    PLAN_CUDA(dev_malloc(&p->d_cell, sizeof(double2) * p->c_pad));
+    IPR_CUDA(acquire_stream(&p->stream));
+    IPR_CUDA(cudaEventCreate(&p->ev0));
+    IPR_CUDA(cudaEventCreate(&p->ev1));
+    IPR_CUDA(dev_malloc(&p->d_cell, sizeof(double2) * p->c_pad));
     // padded so that both the 16-station stages and the 32-station integer k-blocks stay in bounds
     const size_t st_alloc = (size_t)std::max<long long>(p->s_pad + kKT, round_up((p->s_pad + kQKb - 1) / kQKb, kM8Kbs) * kQKb);
-    PLAN_CUDA(dev_malloc(&p->d_st, sizeof(double2) * st_alloc));
-    PLAN_CUDA(dev_malloc(&p->d_obs, sizeof(double) * (size_t)n_dates * n_st));
-    PLAN_CUDA(dev_malloc(&p->d_z0, sizeof(double) * p->z_doubles));
-    PLAN_CUDA(dev_malloc(&p->d_mask, sizeof(double) * p->z_doubles));
-    PLAN_CUDA(dev_malloc(&p->d_flag, (size_t)p->n_gran * kGran));
-    PLAN_CUDA(dev_malloc(&p->d_has_na, (size_t)p->n_gran * kGran));
-    PLAN_CUDA(dev_malloc(&p->d_na_n, sizeof(int) * (size_t)n_dates));
-    PLAN_CUDA(dev_malloc(&p->d_na_idx, sizeof(int) * (size_t)n_dates * kNaCap));
-    PLAN_CUDA(dev_malloc(&p->d_date_mode, (size_t)n_dates));
-    PLAN_CUDA(dev_malloc(&p->d_counters, sizeof(int) * 4));
-    PLAN_CUDA(dev_malloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
-    PLAN_CUDA(dev_malloc(&p->d_wsum, sizeof(double) * p->c_pad));
-    PLAN_CUDA(dev_malloc(&p->d_wmax, sizeof(double) * p->c_pad));
+    IPR_CUDA(dev_malloc(&p->d_st, sizeof(double2) * st_alloc));
+    IPR_CUDA(dev_malloc(&p->d_obs, sizeof(double) * (size_t)n_dates * n_st));
+    IPR_CUDA(dev_malloc(&p->d_z0, sizeof(double) * p->z_doubles));
+    IPR_CUDA(dev_malloc(&p->d_mask, sizeof(double) * p->z_doubles));
+    IPR_CUDA(dev_malloc(&p->d_flag, (size_t)p->n_gran * kGran));
+    IPR_CUDA(dev_malloc(&p->d_has_na, (size_t)p->n_gran * kGran));
+    IPR_CUDA(dev_malloc(&p->d_na_n, sizeof(int) * (size_t)n_dates));
+    IPR_CUDA(dev_malloc(&p->d_na_idx, sizeof(int) * (size_t)n_dates * kNaCap));
+    IPR_CUDA(dev_malloc(&p->d_date_mode, (size_t)n_dates));
+    IPR_CUDA(dev_malloc(&p->d_counters, sizeof(int) * 4));
+    IPR_CUDA(dev_malloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
+    IPR_CUDA(dev_malloc(&p->d_wsum, sizeof(double) * p->c_pad));
+    IPR_CUDA(dev_malloc(&p->d_wmax, sizeof(double) * p->c_pad));
     p->n_kblocks = (int)round_up((p->s_pad + kQKb - 1) / kQKb, kM8Kbs);   // padded: whole pipeline stages
     // default on; the error bound of the digit planes is derived for at most 2^16 stations
     p->int8_mask = !(getenv("IPR_MASK_INT8") && atoi(getenv("IPR_MASK_INT8")) == 0) && n_st <= 65536;
     if (p->int8_mask) {
-        PLAN_CUDA(dev_malloc(&p->d_mask8, (size_t)p->n_gran * p->n_kblocks * kM8BlkBytes));
-        PLAN_CUDA(dev_malloc(&p->d_fb_list, sizeof(int2) * (size_t)p->fb_cap));
-        PLAN_CUDA(dev_malloc(&p->d_fb_count, sizeof(int) * 2));   // [0] list length, [1] sticky overflow flag
-        PLAN_CUDA(cudaMemsetAsync(p->d_fb_count, 0, sizeof(int) * 2, p->stream));
+        IPR_CUDA(dev_malloc(&p->d_mask8, (size_t)p->n_gran * p->n_kblocks * kM8BlkBytes));
+        IPR_CUDA(dev_malloc(&p->d_fb_list, sizeof(int2) * (size_t)p->fb_cap));
+        IPR_CUDA(dev_malloc(&p->d_fb_count, sizeof(int) * 2));   // [0] list length, [1] sticky overflow flag
+        IPR_CUDA(cudaMemsetAsync(p->d_fb_count, 0, sizeof(int) * 2, p->stream));
     }
-    PLAN_CUDA(dev_malloc(&p->d_perm, sizeof(int) * n_st));
-    PLAN_CUDA(dev_malloc(&p->d_run_perm, sizeof(int) * (size_t)(p->c_pad / 8)));
-    PLAN_CUDA(dev_malloc(&p->d_stage_box, sizeof(double4) * (size_t)p->n_stages));
-    PLAN_CUDA(dev_malloc(&p->d_active_total, sizeof(unsigned long long)));
-    PLAN_CUDA(cudaMemsetAsync(p->d_active_total, 0, sizeof(unsigned long long), p->stream));
-    PLAN_CUDA(cudaMemsetAsync(p->d_z0, 0, sizeof(double) * p->z_doubles, p->stream));
-    PLAN_CUDA(cudaMemsetAsync(p->d_mask, 0, sizeof(double) * p->z_doubles, p->stream));
-    PLAN_CUDA(cudaMemsetAsync(p->d_flag, 0, (size_t)p->n_gran * kGran, p->stream));
-    PLAN_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(int) * 4, p->stream));
+    IPR_CUDA(dev_malloc(&p->d_perm, sizeof(int) * n_st));
+    IPR_CUDA(dev_malloc(&p->d_run_perm, sizeof(int) * (size_t)(p->c_pad / 8)));
+    IPR_CUDA(dev_malloc(&p->d_stage_box, sizeof(double4) * (size_t)p->n_stages));
+    IPR_CUDA(dev_malloc(&p->d_active_total, sizeof(unsigned long long)));
+    IPR_CUDA(cudaMemsetAsync(p->d_active_total, 0, sizeof(unsigned long long), p->stream));
+    IPR_CUDA(cudaMemsetAsync(p->d_z0, 0, sizeof(double) * p->z_doubles, p->stream));
+    IPR_CUDA(cudaMemsetAsync(p->d_mask, 0, sizeof(double) * p->z_doubles, p->stream));
+    IPR_CUDA(cudaMemsetAsync(p->d_flag, 0, (size_t)p->n_gran * kGran, p->stream));
+    IPR_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(int) * 4, p->stream));
     {
         std::vector<double2> h(p->c_pad);
         for (long long i = 0; i < p->c_pad; i++) {
             const long long k = std::min<long long>(i, n_cells - 1);
             h[i] = make_double2(canon_zero(cell_x[k]), canon_zero(cell_y[k]));
             if (!std::isfinite(h[i].x) || !std::isfinite(h[i].y)) {
-                ipr_plan_destroy(p);
                 set_err(err, errlen, "cell coordinate %lld is not finite", k);
                 return IPR_EINVAL;
             }
         }
-        PLAN_CUDA(cudaMemcpyAsync(p->d_cell, h.data(), sizeof(double2) * p->c_pad, cudaMemcpyHostToDevice, p->stream));
-        // cell tiles for Cressman: 8 Morton-consecutive runs of 8 consecutive cells, i.e. compact
-        // 2-D patches instead of 64 x 1 strips, so that fewer station stages reach any cell of a tile
-        std::vector<int> run_perm;
-        {
-            const int n_runs = (int)(p->c_pad / 8);
-            std::vector<double> rx(n_runs), ry(n_runs);
-            for (int i = 0; i < n_runs; i++) {
-                rx[i] = h[(size_t)i * 8].x;
-                ry[i] = h[(size_t)i * 8].y;
-            }
-            run_perm = morton_order(rx.data(), ry.data(), n_runs);
-        }
-        PLAN_CUDA(cudaMemcpyAsync(p->d_run_perm, run_perm.data(), sizeof(int) * run_perm.size(), cudaMemcpyHostToDevice,
-                                  p->stream));
-        PLAN_CUDA(cudaStreamSynchronize(p->stream));
+        IPR_CUDA(cudaMemcpyAsync(p->d_cell, h.data(), sizeof(double2) * p->c_pad, cudaMemcpyHostToDevice, p->stream));
+        // cell tiles for Cressman are 8 Morton-consecutive runs of 8 consecutive cells (ensure_run_perm);
+        // the sort costs ~10 ms per 10^6 cells on the host, so it waits for the first Cressman call
+        p->h_run_xy.resize((size_t)(p->c_pad / 8));
+        for (size_t i = 0; i < p->h_run_xy.size(); i++) p->h_run_xy[i] = h[i * 8];
+        IPR_CUDA(cudaStreamSynchronize(p->stream));
         for (int i = 0; i < n_st; i++) {
             if (!std::isfinite(st_x[i]) || !std::isfinite(st_y[i])) {
-                ipr_plan_destroy(p);
                 set_err(err, errlen, "station coordinate %d is not finite", i);
                 return IPR_EINVAL;
             }
@@ -836,7 +867,7 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
         std::vector<int> perm = morton_order(st_x, st_y, n_st);
         std::vector<double2> hs(st_alloc, make_double2(kPadCoord, kPadCoord));
         for (int i = 0; i < n_st; i++) hs[i] = make_double2(canon_zero(st_x[perm[i]]), canon_zero(st_y[perm[i]]));
-        PLAN_CUDA(cudaMemcpyAsync(p->d_perm, perm.data(), sizeof(int) * n_st, cudaMemcpyHostToDevice, p->stream));
+        IPR_CUDA(cudaMemcpyAsync(p->d_perm, perm.data(), sizeof(int) * n_st, cudaMemcpyHostToDevice, p->stream));
         std::vector<double4> boxes(p->n_stages);
         for (int st = 0; st < p->n_stages; st++) {
             double4 b = make_double4(hs[(size_t)st * kKT].x, hs[(size_t)st * kKT].y, hs[(size_t)st * kKT].x,
@@ -850,20 +881,23 @@ int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const dou
             }
             boxes[st] = b;
         }
-        PLAN_CUDA(cudaMemcpyAsync(p->d_stage_box, boxes.data(), sizeof(double4) * boxes.size(), cudaMemcpyHostToDevice,
+        IPR_CUDA(cudaMemcpyAsync(p->d_stage_box, boxes.data(), sizeof(double4) * boxes.size(), cudaMemcpyHostToDevice,
                                   p->stream));
-        PLAN_CUDA(cudaStreamSynchronize(p->stream));
-        PLAN_CUDA(cudaMemcpyAsync(p->d_st, hs.data(), sizeof(double2) * hs.size(), cudaMemcpyHostToDevice, p->stream));
-        PLAN_CUDA(cudaStreamSynchronize(p->stream));  // staging vectors go out of scope
+        IPR_CUDA(cudaStreamSynchronize(p->stream));
+        IPR_CUDA(cudaMemcpyAsync(p->d_st, hs.data(), sizeof(double2) * hs.size(), cudaMemcpyHostToDevice, p->stream));
+        IPR_CUDA(cudaStreamSynchronize(p->stream));  // staging vectors go out of scope
     }
-#undef PLAN_CUDA
-    int rc = scan_zero_pairs(p, err, errlen);
-    if (rc != IPR_OK) {
-        ipr_plan_destroy(p);
-        return rc;
-    }
-    *plan = p;
+    const int rc = scan_zero_pairs(p, err, errlen);
+    if (rc != IPR_OK) return rc;
+    *plan = holder.release();
     return IPR_OK;
+}
+
+int ipr_plan_create(ipr_plan** plan, int device, const double* cell_x, const double* cell_y, int64_t n_cells,
+                    const double* st_x, const double* st_y, int32_t n_st, int32_t n_dates, char* err, size_t errlen) {
+    return no_throw(err, errlen, [&] {
+        return plan_create_impl(plan, device, cell_x, cell_y, n_cells, st_x, st_y, n_st, n_dates, err, errlen);
+    });
 }
 
 void ipr_plan_destroy(ipr_plan* p) {
@@ -919,7 +953,7 @@ static int plan_set_obs_ld(ipr_plan* p, const double* obs, long long ld, char* e
 }
 
 int ipr_plan_set_obs(ipr_plan* p, const double* obs, char* err, size_t errlen) {
-    return plan_set_obs_ld(p, obs, p ? p->n_dates : 0, err, errlen);
+    return no_throw(err, errlen, [&] { return plan_set_obs_ld(p, obs, p ? p->n_dates : 0, err, errlen); });
 }
 
 int ipr_plan_set_obs_device(ipr_plan* p, const double* d_obs, char* err, size_t errlen) {
@@ -930,11 +964,11 @@ int ipr_plan_set_obs_device(ipr_plan* p, const double* d_obs, char* err, size_t 
     IPR_CUDA(cudaSetDevice(p->device));
     IPR_CUDA(cudaMemcpyAsync(p->d_obs, d_obs, sizeof(double) * (size_t)p->n_dates * p->n_st, cudaMemcpyDeviceToDevice,
                              p->stream));
-    return prepare_obs(p, err, errlen);
+    return no_throw(err, errlen, [&] { return prepare_obs(p, err, errlen); });
 }
 
-int ipr_plan_idw(ipr_plan* p, double pw, int32_t t0, int32_t t1, double* d_out, int64_t ld_out, char* err,
-                 size_t errlen) {
+static int plan_idw_impl(ipr_plan* p, double pw, int32_t t0, int32_t t1, double* d_out, int64_t ld_out, char* err,
+                         size_t errlen) {
     int rc = check_range(p, t0, t1, d_out, ld_out, err, errlen);
     if (rc) return rc;
     if (!(pw > 0) || !std::isfinite(pw)) {
@@ -985,6 +1019,11 @@ int ipr_plan_idw(ipr_plan* p, double pw, int32_t t0, int32_t t1, double* d_out, 
     return run_post(p, t0, t1, d_out, ld_out, err, errlen);
 }
 
+int ipr_plan_idw(ipr_plan* p, double pw, int32_t t0, int32_t t1, double* d_out, int64_t ld_out, char* err,
+                 size_t errlen) {
+    return no_throw(err, errlen, [&] { return plan_idw_impl(p, pw, t0, t1, d_out, ld_out, err, errlen); });
+}
+
 int ipr_plan_set_post(ipr_plan* p, int32_t round_mode, int32_t n_round, const uint8_t* cell_keep, char* err,
                       size_t errlen) {
     if (!p) {
@@ -1009,8 +1048,8 @@ int ipr_plan_set_post(ipr_plan* p, int32_t round_mode, int32_t n_round, const ui
     return IPR_OK;
 }
 
-int ipr_plan_cressman(ipr_plan* p, const double* radii_m, int32_t n_radii, int32_t t0, int32_t t1, double* d_out,
-                      int64_t ld_out, int64_t stack_stride, char* err, size_t errlen) {
+static int plan_cressman_impl(ipr_plan* p, const double* radii_m, int32_t n_radii, int32_t t0, int32_t t1,
+                              double* d_out, int64_t ld_out, int64_t stack_stride, char* err, size_t errlen) {
     int rc = check_range(p, t0, t1, d_out, ld_out, err, errlen);
     if (rc) return rc;
     if (!radii_m || n_radii <= 0) {
@@ -1034,6 +1073,13 @@ int ipr_plan_cressman(ipr_plan* p, const double* radii_m, int32_t n_radii, int32
         if ((rc = run_post(p, t0, t1, d_out + (size_t)ri * stack_stride, ld_out, err, errlen))) return rc;
     }
     return IPR_OK;
+}
+
+int ipr_plan_cressman(ipr_plan* p, const double* radii_m, int32_t n_radii, int32_t t0, int32_t t1, double* d_out,
+                      int64_t ld_out, int64_t stack_stride, char* err, size_t errlen) {
+    return no_throw(err, errlen, [&] {
+        return plan_cressman_impl(p, radii_m, n_radii, t0, t1, d_out, ld_out, stack_stride, err, errlen);
+    });
 }
 
 int ipr_plan_stage_blocks(ipr_plan* p, uint64_t* executed, uint64_t* dense) {
@@ -1198,6 +1244,11 @@ public:
 
     int finish() {
         if (!started_) {
+            for (int i = 0; i < kSlots; i++)
+                if (ev_[i]) {
+                    cudaEventDestroy(ev_[i]);
+                    ev_[i] = nullptr;
+                }
             release_slots();
             return IPR_OK;
         }
@@ -1208,7 +1259,10 @@ public:
         cv_.notify_all();
         if (drain_.joinable()) drain_.join();
         for (int i = 0; i < kSlots; i++)
-            if (ev_[i]) cudaEventDestroy(ev_[i]);
+            if (ev_[i]) {
+                cudaEventDestroy(ev_[i]);
+                ev_[i] = nullptr;
+            }
         release_slots();
         started_ = false;
         return failed_ ? IPR_ECUDA : IPR_OK;
@@ -1313,6 +1367,7 @@ int run_device_block(const HostJob& job, int device, long long c0, long long c1,
         ~Guard() {
             Trace td;
             cudaSetDevice(p->device);
+            if (p->stream) cudaStreamSynchronize(p->stream);   // kernels may still write the ring on an error return
             if (copy) {
                 cudaStreamSynchronize(copy);
                 release_stream(copy);   // synchronised just above
@@ -1343,7 +1398,17 @@ int run_device_block(const HostJob& job, int device, long long c0, long long c1,
     struct Item { int stack, t0, t1; };
     std::vector<Item> items;
     for (int s = 0; s < n_stacks; s++)
-        for (int t = 0; t < nd; t += chunk) items.push_back({s, t, std::min(nd, t + chunk)});
+        for (int t = 0; t < nd; t += chunk) {
+            const int te = std::min(nd, t + chunk);
+            // the very first granule goes out as 32 + 96 dates: the copy engine starts after a quarter of
+            // a granule's kernels instead of a whole one (nothing else can overlap with that wait)
+            if (s == 0 && t == 0 && te > 32) {
+                items.push_back({s, 0, 32});
+                items.push_back({s, 32, te});
+            } else {
+                items.push_back({s, t, te});
+            }
+        }
     const size_t slot_doubles = (size_t)nc * std::min(chunk, (int)round_up(nd, 16));
     IPR_CUDA(acquire_stream(&g.copy));
     PageableSink sink;
@@ -1437,12 +1502,16 @@ int run_host_job(const HostJob& job, const int* devices, int n_devices, char* er
     }
     std::vector<int> rcs(G, IPR_OK);
     std::vector<std::string> errs(G, std::string(256, '\0'));
+    auto run_block = [&](int g) {
+        char* e = &errs[g][0];
+        const size_t n = errs[g].size();
+        rcs[g] = no_throw(e, n, [&] { return run_device_block(jobx, devs[g], bounds[g], bounds[g + 1], e, n); });
+    };
     if (G == 1) {
-        rcs[0] = run_device_block(jobx, devs[0], bounds[0], bounds[1], &errs[0][0], errs[0].size());
+        run_block(0);
     } else {
         std::vector<std::thread> th;
-        for (int g = 0; g < G; g++)
-            th.emplace_back([&, g] { rcs[g] = run_device_block(jobx, devs[g], bounds[g], bounds[g + 1], &errs[g][0], errs[g].size()); });
+        for (int g = 0; g < G; g++) th.emplace_back(run_block, g);
         for (auto& t : th) t.join();
     }
     tj.mark("(job) all device blocks done");
@@ -1462,7 +1531,7 @@ int ipr_idw_f64(const double* cell_x, const double* cell_y, int64_t n_cells, con
                 int32_t n_st, const double* obs, int32_t n_dates, double p, const int* devices, int n_devices,
                 double* out, char* err, size_t errlen) {
     HostJob job{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, false, p, nullptr, 0, out};
-    return run_host_job(job, devices, n_devices, err, errlen);
+    return no_throw(err, errlen, [&] { return run_host_job(job, devices, n_devices, err, errlen); });
 }
 
 int ipr_idw_post_f64(const double* cell_x, const double* cell_y, int64_t n_cells, const double* st_x,
@@ -1473,7 +1542,7 @@ int ipr_idw_post_f64(const double* cell_x, const double* cell_y, int64_t n_cells
     job.round_mode = round_mode;
     job.n_round = n_round;
     job.cell_keep = cell_keep;
-    return run_host_job(job, devices, n_devices, err, errlen);
+    return no_throw(err, errlen, [&] { return run_host_job(job, devices, n_devices, err, errlen); });
 }
 
 int ipr_cressman_post_f64(const double* cell_x, const double* cell_y, int64_t n_cells, const double* st_x,
@@ -1489,7 +1558,7 @@ int ipr_cressman_post_f64(const double* cell_x, const double* cell_y, int64_t n_
     job.round_mode = round_mode;
     job.n_round = n_round;
     job.cell_keep = cell_keep;
-    return run_host_job(job, devices, n_devices, err, errlen);
+    return no_throw(err, errlen, [&] { return run_host_job(job, devices, n_devices, err, errlen); });
 }
 
 int ipr_cressman_f64(const double* cell_x, const double* cell_y, int64_t n_cells, const double* st_x,
@@ -1500,7 +1569,7 @@ int ipr_cressman_f64(const double* cell_x, const double* cell_y, int64_t n_cells
         return IPR_EINVAL;
     }
     HostJob job{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, true, 2.0, radii_m, n_radii, out};
-    return run_host_job(job, devices, n_devices, err, errlen);
+    return no_throw(err, errlen, [&] { return run_host_job(job, devices, n_devices, err, errlen); });
 }
 
 }  // extern "C"

@@ -451,6 +451,19 @@ def test_weight_cache_chunking_and_reset(monkeypatch):
     plan.close()
 
 
+@pytest.mark.parametrize("int8", ["1", "0"])
+def test_weight_cache_chunking_with_masked_granules(monkeypatch, int8):
+    """Heavy NA (masked granules) while the A-operand cache holds only a few cell tiles at a time:
+    every chunk of cell tiles must get its masked granules, on the int8 mask path and on the FP64 one."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(70, 41, 130, 300, na_frac=0.25, plant_zero_dist=3, seed=17)
+    monkeypatch.setenv("IPR_MASK_INT8", int8)
+    want = engine.idw_grid(cx, cy, sx, sy, obs, p=2.0)
+    assert_parity(want, ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="unchunked")
+    monkeypatch.setenv("IPR_WCACHE_MB", "1")
+    got = engine.idw_grid(cx, cy, sx, sy, obs, p=2.0)
+    assert np.array_equal(got, want, equal_nan=True)
+
+
 @pytest.mark.parametrize("n_dates", [300, 70, 20])
 def test_multi_device_scheduler_on_one_gpu(n_dates):
     """The multi-GPU scheduler of the host-buffer entry points (contiguous cell ranges per device,
