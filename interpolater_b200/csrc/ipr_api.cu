@@ -1,7 +1,7 @@
 // interpolater_b200 — C ABI implementation: device-resident plan, kernel scheduling, and the
 // one-shot host-buffer entry points with the multi-GPU scheduler (cell ranges per device).
 // See include/interpolater_b200.h for the contract and the reference lines each call replaces.
-#include "../../include/interpolater_b200.h"
+#include "interpolater_b200.h"   // include/ (build adds -I)
 
 #include <algorithm>
 #include <condition_variable>

@@ -9,8 +9,9 @@
  *   C_ipr_cressman(cell_x, cell_y, st_x, st_y, obs, radii_m, devices) -> n_cells x n_dates x n_radii array
  *
  * obs is the n_dates x n_stations double matrix (column-major, NA = missing) whose columns are
- * aligned with st_x/st_y.  The result is an R-allocated REALSXP that the core fills in place
- * (it pins it with cudaHostRegister for the duration of the call); NA cells carry NA_real_.
+ * aligned with st_x/st_y.  The result is an R-allocated (pageable) REALSXP that the core fills in
+ * place through its pinned staging ring; NA cells carry NA_real_.  The call blocks until the result
+ * is complete (no R_CheckUserInterrupt inside).
  * The core never calls into R; on failure the shim raises an R error AFTER the core has cleaned up.
  */
 #include <R.h>
