@@ -14,6 +14,8 @@
  * is complete (no R_CheckUserInterrupt inside).
  * The core never calls into R; on failure the shim raises an R error AFTER the core has cleaned up.
  */
+#include <limits.h>
+
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
@@ -41,6 +43,7 @@ SEXP C_ipr_idw(SEXP cell_x, SEXP cell_y, SEXP st_x, SEXP st_y, SEXP obs, SEXP p,
     const R_xlen_t n_cells = XLENGTH(cell_x);
     const int n_st = LENGTH(st_x);
     if (XLENGTH(cell_y) != n_cells || LENGTH(st_y) != n_st) error("coordinate vectors differ in length");
+    if (n_cells > INT_MAX) error("more than 2^31 - 1 cells: a matrix dimension cannot hold that");
     if (!isMatrix(obs) || ncols(obs) != n_st) error("obs must be an n_dates x n_stations matrix");
     const int n_dates = nrows(obs);
     int* dev = NULL;
@@ -61,6 +64,7 @@ SEXP C_ipr_cressman(SEXP cell_x, SEXP cell_y, SEXP st_x, SEXP st_y, SEXP obs, SE
     const R_xlen_t n_cells = XLENGTH(cell_x);
     const int n_st = LENGTH(st_x);
     if (XLENGTH(cell_y) != n_cells || LENGTH(st_y) != n_st) error("coordinate vectors differ in length");
+    if (n_cells > INT_MAX) error("more than 2^31 - 1 cells: a matrix dimension cannot hold that");
     if (!isMatrix(obs) || ncols(obs) != n_st) error("obs must be an n_dates x n_stations matrix");
     const int n_dates = nrows(obs);
     const int n_radii = LENGTH(radii_m);
