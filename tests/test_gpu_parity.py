@@ -536,3 +536,62 @@ def test_full_size_properties():
     got = out1[:6][:, torch.from_numpy(idx).cuda()].cpu().numpy().T
     assert_parity(got, want, label="full-size sample")                      # (iv)
     plan.close()
+
+
+def test_full_size_properties_masked_and_cressman():
+    """The same 1,000,000 x 2,000 geometry with 20 % NA (masked contraction, int8 mask GEMM) and
+    through Cressman with the cfg-4 radii: station-constant fields, bounds, NA pattern, linearity,
+    and a sample of cells against the oracle — all reduced on the device."""
+    import torch
+
+    ncol = nrow = 1000
+    n_st, n_dates = 2000, 256
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(ncol, nrow, n_st, n_dates, na_frac=0.2, plant_zero_dist=5,
+                                                   all_na_dates=(7,), all_zero_dates=(130,))
+    navail = np.isfinite(obs)
+    const = np.linspace(0.5, 40.0, n_dates)
+    z2 = np.where(navail, const[:, None], np.nan)               # constant over the available stations
+    plan = engine.Plan(0, cx, cy, sx, sy, n_dates)
+    out1 = torch.empty((n_dates, cx.size), dtype=torch.float64, device="cuda")
+    out2 = torch.empty_like(out1)
+    plan.set_obs(obs)
+    plan.idw(out1.data_ptr())
+    plan.set_obs(z2)
+    plan.idw(out2.data_ptr())
+    plan.sync()
+    # --- masked IDW
+    assert bool(out1[7].isnan().all()) and bool(out2[7].isnan().all())          # all-NA date
+    assert bool((out1[130] == 0).all())                                         # exact-zero layer
+    live = [t for t in range(n_dates) if t != 7]
+    c = torch.from_numpy(const).cuda()[:, None]
+    assert not bool(out2[live].isnan().any())
+    assert float(((out2[live] - c[live]).abs() / c[live]).max()) < 1e-9         # constant field
+    lo = torch.from_numpy(np.nanmin(obs[live], axis=1)).cuda()[:, None]
+    hi = torch.from_numpy(np.nanmax(obs[live], axis=1)).cuda()[:, None]
+    assert bool(((out1[live] >= lo - 1e-9) & (out1[live] <= hi + 1e-9)).all())
+    idx = np.random.default_rng(1).choice(cx.size, 1200, replace=False)
+    dates = [0, 7, 63, 64, 130, 255]
+    want = ref.idw_reference(cx[idx], cy[idx], sx, sy, obs[dates], 2.0)
+    got = out1[dates][:, torch.from_numpy(idx).cuda()].cpu().numpy().T
+    assert_parity(got, want, label="full-size masked sample")
+    del out2
+    # --- Cressman, cfg-4 radii; the denominator ignores availability, so out <= max and the NA
+    # pattern is the same on every date
+    radii = np.array([25e3, 50e3, 100e3, 200e3])
+    outc = torch.empty((radii.size, n_dates, cx.size), dtype=torch.float64, device="cuda")
+    plan.set_obs(obs)
+    plan.cressman(outc.data_ptr(), radii)
+    plan.sync()
+    nanmap = outc.isnan()
+    assert bool((nanmap == nanmap[:, :1]).all())
+    frac_na = nanmap[:, 0].double().mean(dim=1).cpu().numpy()
+    assert frac_na[0] > 0.0 and np.all(np.diff(frac_na) <= 0) and frac_na[-1] == 0.0   # small radii leave holes
+    hi_all = torch.from_numpy(np.nanmax(np.where(navail, obs, 0.0), axis=1)).cuda()[None, :, None]
+    ok = nanmap | ((outc >= -1e-9) & (outc <= hi_all + 1e-9))
+    assert bool(ok.all())
+    assert bool((outc[:, 7][~nanmap[:, 7]] == 0).all())                         # all-NA date -> 0 where in range
+    wantc = ref.cressman_reference(cx[idx], cy[idx], sx, sy, obs[dates], radii)
+    gotc = outc[:, dates][:, :, torch.from_numpy(idx).cuda()].cpu().numpy()
+    for ri in range(radii.size):
+        assert_parity(gotc[ri].T, wantc[ri], label=f"full-size Cressman sample R={radii[ri]:.0f}")
+    plan.close()
