@@ -141,10 +141,12 @@ int ipr_plan_timer_start(ipr_plan* plan);
 int ipr_plan_timer_stop(ipr_plan* plan, float* elapsed_ms); /* synchronises */
 /* counters since plan creation: kernels launched by this library on the plan's stream */
 int64_t ipr_plan_launch_count(const ipr_plan* plan);
-/* Cumulative counts, since plan creation, of (64-cell tile, 32-station stage) blocks of the A
- * operand: `dense` = what the dense product visits, `executed` = blocks holding any non-zero weight
- * (all of them for IDW; for Cressman the blocks wholly beyond the radius are skipped).  Lets a
- * caller report executed vs dense-equivalent flops.  Synchronises the plan stream. */
+/* Cumulative counts, since plan creation, of (64-cell tile, station stage) blocks of the A
+ * operand — 16-station stages for IDW, 8-station half stages for Cressman: `dense` = what the dense
+ * product visits, `executed` = blocks holding any non-zero weight (all of them for IDW; for Cressman
+ * the blocks wholly beyond the radius are skipped).  Only the ratio of differences taken around
+ * calls of ONE kind is meaningful; it lets a caller report executed vs dense-equivalent flops.
+ * Synchronises the plan stream. */
 int ipr_plan_stage_blocks(ipr_plan* plan, uint64_t* executed, uint64_t* dense);
 /* number of (cell, station) pairs at exactly zero distance found for this geometry */
 int64_t ipr_plan_zero_pairs(const ipr_plan* plan);

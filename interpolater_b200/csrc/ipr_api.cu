@@ -288,11 +288,11 @@ struct TileSets {
 };
 void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, TileSets& ts);
 
-template <int NP, bool MASKED>
+template <int NP, bool MASKED, int KSTEPS = kKSteps>
 int launch_contract(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles, char* err, size_t errlen) {
-    using L = SmemLayout<MASKED>;
+    using L = SmemLayout<MASKED, KSTEPS>;
     static bool configured[64] = {false};
-    auto kern = contract_kernel<NP, MASKED>;
+    auto kern = contract_kernel<NP, MASKED, false, KSTEPS>;
     if (!configured[p->device & 63]) {
         IPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         configured[p->device & 63] = true;
@@ -343,7 +343,8 @@ int ensure_weights(ipr_plan* p, int mode, const WeightParams& wp, int tile0, int
     w.active_total = p->d_active_total;
     w.run_perm = (mode == kCressman) ? p->d_run_perm : nullptr;
     w.stage_box = (mode == kCressman) ? p->d_stage_box : nullptr;
-    p->stage_tiles_total += (unsigned long long)n_tiles * p->n_stages;
+    // Cressman lists (and counts) half stages
+    p->stage_tiles_total += (unsigned long long)n_tiles * p->n_stages * (mode == kCressman ? kSubStages : 1);
     w.cell_tile0 = tile0;
     w.n_cell_tiles = n_tiles;
     w.n_stages = p->n_stages;
@@ -388,7 +389,7 @@ int ensure_wcache(ipr_plan* p, bool need_wq, char* err, size_t errlen) {
         return IPR_ENOMEM;
     }
     cudaError_t e = dev_malloc(&p->d_wfrag, tile_bytes * tiles);
-    if (e == cudaSuccess) e = dev_malloc(&p->d_stage_list, sizeof(int) * (size_t)tiles * p->n_stages);
+    if (e == cudaSuccess) e = dev_malloc(&p->d_stage_list, sizeof(int) * (size_t)tiles * p->n_stages * kSubStages);
     if (e == cudaSuccess) e = dev_malloc(&p->d_n_active, sizeof(int) * (size_t)tiles);
     if (e == cudaSuccess && need_wq)
         e = dev_malloc(&p->d_wq, sizeof(uint4) * (size_t)tiles * p->n_kblocks * kQTileKbU4);
@@ -555,6 +556,14 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
         // masked granules through the error-free int8 mask contraction (every chunk of cell tiles)
         const bool use_int8 = masked_here && p->int8_mask && p->d_wq != nullptr;
         if (use_int8 && (rc = run_int8_masked(p, mode, wp, a, ts, t0, t1, err, errlen))) return rc;
+        if (mode == kCressman) {   // half stages (8 stations): finer active lists
+            constexpr int K = kCressmanKSteps;
+            if (!ts.u[8].empty() && (rc = launch_contract<8, false, K>(p, a, ts.u[8], err, errlen))) return rc;
+            if (!ts.u[6].empty() && (rc = launch_contract<6, false, K>(p, a, ts.u[6], err, errlen))) return rc;
+            if (!ts.u[4].empty() && (rc = launch_contract<4, false, K>(p, a, ts.u[4], err, errlen))) return rc;
+            if (!ts.u[2].empty() && (rc = launch_contract<2, false, K>(p, a, ts.u[2], err, errlen))) return rc;
+            continue;
+        }
         if (!ts.u[8].empty() && (rc = launch_contract<8, false>(p, a, ts.u[8], err, errlen))) return rc;
         if (!ts.u[6].empty() && (rc = launch_contract<6, false>(p, a, ts.u[6], err, errlen))) return rc;
         if (!ts.u[4].empty() && (rc = launch_contract<4, false>(p, a, ts.u[4], err, errlen))) return rc;
@@ -832,7 +841,7 @@ static int plan_create_impl(ipr_plan** plan, int device, const double* cell_x, c
     }
     IPR_CUDA(dev_malloc(&p->d_perm, sizeof(int) * n_st));
     IPR_CUDA(dev_malloc(&p->d_run_perm, sizeof(int) * (size_t)(p->c_pad / 8)));
-    IPR_CUDA(dev_malloc(&p->d_stage_box, sizeof(double4) * (size_t)p->n_stages));
+    IPR_CUDA(dev_malloc(&p->d_stage_box, sizeof(double4) * (size_t)p->n_stages * kSubStages));
     IPR_CUDA(dev_malloc(&p->d_active_total, sizeof(unsigned long long)));
     IPR_CUDA(cudaMemsetAsync(p->d_active_total, 0, sizeof(unsigned long long), p->stream));
     IPR_CUDA(cudaMemsetAsync(p->d_z0, 0, sizeof(double) * p->z_doubles, p->stream));
@@ -868,18 +877,19 @@ static int plan_create_impl(ipr_plan** plan, int device, const double* cell_x, c
         std::vector<double2> hs(st_alloc, make_double2(kPadCoord, kPadCoord));
         for (int i = 0; i < n_st; i++) hs[i] = make_double2(canon_zero(st_x[perm[i]]), canon_zero(st_y[perm[i]]));
         IPR_CUDA(cudaMemcpyAsync(p->d_perm, perm.data(), sizeof(int) * n_st, cudaMemcpyHostToDevice, p->stream));
-        std::vector<double4> boxes(p->n_stages);
-        for (int st = 0; st < p->n_stages; st++) {
-            double4 b = make_double4(hs[(size_t)st * kKT].x, hs[(size_t)st * kKT].y, hs[(size_t)st * kKT].x,
-                                     hs[(size_t)st * kKT].y);
-            for (int k = 1; k < kKT; k++) {
-                const double2 c = hs[(size_t)st * kKT + k];
+        // bounding box of every half stage (the granularity of Cressman's active lists)
+        constexpr int kHalf = kKT / kSubStages;
+        std::vector<double4> boxes((size_t)p->n_stages * kSubStages);
+        for (size_t hb = 0; hb < boxes.size(); hb++) {
+            double4 b = make_double4(hs[hb * kHalf].x, hs[hb * kHalf].y, hs[hb * kHalf].x, hs[hb * kHalf].y);
+            for (int k = 1; k < kHalf; k++) {
+                const double2 c = hs[hb * kHalf + k];
                 b.x = std::min(b.x, c.x);
                 b.y = std::min(b.y, c.y);
                 b.z = std::max(b.z, c.x);
                 b.w = std::max(b.w, c.y);
             }
-            boxes[st] = b;
+            boxes[hb] = b;
         }
         IPR_CUDA(cudaMemcpyAsync(p->d_stage_box, boxes.data(), sizeof(double4) * boxes.size(), cudaMemcpyHostToDevice,
                                   p->stream));

@@ -51,6 +51,12 @@ constexpr int kBlkDoubles = kKT * kGranLd;
 constexpr int kBlkBytes = kBlkDoubles * 8;
 // A operand cache: weights in fragment order, [cell tile][stage][k-step][warp][lane]
 constexpr int kWStageDoubles = kKSteps * kThreads;
+// Cressman walks the station axis in HALF stages (2 k-steps = 8 stations): both operand layouts
+// are k-step-major inside a stage, so a half stage is a contiguous half of the same A chunk / B
+// block and the finer list skips more of the exactly-zero product (measured -12 % on cfg 4; IDW,
+// which visits every stage anyway, lost 2.6 % with 8-station stages and keeps 16).
+constexpr int kSubStages = 2;
+constexpr int kCressmanKSteps = kKSteps / kSubStages;
 constexpr double kPadCoord = 1e150;                  // padded stations: d^2 ~ 2e300 -> weight ~ 0
 constexpr unsigned long long kNaRealBits = 0x7FF00000000007A2ull;
 
@@ -74,7 +80,8 @@ struct TileList {
 struct ContractArgs {
     const double* wfrag;      // A operand cache for cell tiles [cell_tile0, cell_tile0 + n_cell_tiles)
     const double* wsum;       // [c_pad] per-cell sum of weights over all stations
-    const int* stage_list;    // [n_cell_tiles][n_stages] stages holding any non-zero weight, ascending
+    const int* stage_list;    // [n_cell_tiles][kSubStages * n_stages] (half) stages holding any non-zero weight,
+                              // ascending, in units of the instantiation's KSTEPS k-steps
     const int* n_active;      // [n_cell_tiles] length of each list
     const int* run_perm;      // nullptr, or [c_pad/8]: warp w of cell tile T owns the 8 consecutive cells
                               // of run run_perm[8T + w] (spatially compact tiles for Cressman)
@@ -96,11 +103,11 @@ struct WeightArgs {
     double* wfrag;            // chunk base
     double* wsum;             // [c_pad]
     double* wmax;             // [c_pad] largest weight of the cell (row scale of the int8 slices)
-    int* stage_list;          // [n_cell_tiles][n_stages]
+    int* stage_list;          // [n_cell_tiles][kSubStages * n_stages]
     int* n_active;            // [n_cell_tiles]
     const int* run_perm;      // see ContractArgs
-    const double4* stage_box; // nullptr, or [n_stages] bounding box (xmin, ymin, xmax, ymax) of each stage's
-                              // stations: Cressman skips stages whose box is farther than R from the tile's
+    const double4* stage_box; // nullptr, or [kSubStages * n_stages] bounding box (xmin, ymin, xmax, ymax) of each
+                              // half stage's stations: Cressman skips those farther than R from the tile's box
     unsigned long long* active_total;  // cumulative count of active (cell tile, stage) blocks
     int cell_tile0, n_cell_tiles;
     int n_stages;
@@ -190,31 +197,35 @@ __device__ __forceinline__ double weight_from_d2(double d2, const WeightParams& 
     }
 }
 
-template <bool MASKED>
+template <bool MASKED, int KSTEPS = kKSteps>
 struct SmemLayout {
     static constexpr int kBlocks = MASKED ? 2 : 1;   // granule blocks per stage (z0 [+ mask])
-    static constexpr int kStages = MASKED ? 3 : 5;   // pipeline depth (two CTAs share the SM's 227 KB)
-    static constexpr int kStageBytes = kBlocks * kBlkBytes;
+    // pipeline depth (two CTAs share the SM's 227 KB); half stages: same bytes in flight
+    static constexpr int kStages = MASKED ? 3 : (KSTEPS == kKSteps ? 5 : 8);
+    static constexpr int kPartDoubles = KSTEPS * 4 * kGranLd;   // one (half) block: KSTEPS*4 station rows
+    static constexpr int kPartBytes = kPartDoubles * 8;
+    static constexpr int kStageBytes = kBlocks * kPartBytes;
     static constexpr int kBarOff = kStageBytes * kStages;
     static constexpr int kTotal = kBarOff + kStages * 8 + kStages * 4 + 16;
-    static constexpr uint32_t kTxBytes = kBlocks * kBlkBytes;
+    static constexpr uint32_t kTxBytes = kBlocks * kPartBytes;
 };
 
 // Refill one pipeline stage: one bulk copy (TMA bulk engine) per granule block.  Called by one lane.
 // it = position in the tile's active-stage list (selects the slot), sid = the stage itself.
-template <bool MASKED>
+template <bool MASKED, int KSTEPS>
 __device__ __forceinline__ void produce_stage(const ContractArgs& args, unsigned char* smem, uint64_t* full_bar,
                                               int it, int sid, int gran0) {
-    using L = SmemLayout<MASKED>;
+    using L = SmemLayout<MASKED, KSTEPS>;
     const int slot = it % L::kStages;
     unsigned char* stage = smem + slot * L::kStageBytes;
     // generic-proxy reads of this slot (all warps, ordered by the release counter) precede the
     // async-proxy writes issued below
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&full_bar[slot], L::kTxBytes);
-    const size_t b0 = ((size_t)gran0 * args.n_stages + sid) * kBlkDoubles;
-    bulk_g2s(stage, args.z0 + b0, kBlkBytes, &full_bar[slot]);
-    if (MASKED) bulk_g2s(stage + kBlkBytes, args.mask + b0, kBlkBytes, &full_bar[slot]);
+    // blocks of a granule are contiguous and rows are k-step-major: (half) stage sid starts sid parts in
+    const size_t b0 = (size_t)gran0 * args.n_stages * kBlkDoubles + (size_t)sid * L::kPartDoubles;
+    bulk_g2s(stage, args.z0 + b0, L::kPartBytes, &full_bar[slot]);
+    if (MASKED) bulk_g2s(stage + L::kPartBytes, args.mask + b0, L::kPartBytes, &full_bar[slot]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -234,8 +245,11 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
     const long long run = args.run_perm ? (long long)__ldg(args.run_perm + (size_t)ct * 8 + warp) : (long long)ct * 8 + warp;
     const long long cell = run * 8 + r;
     const double2 cxy = args.cell_xy[cell];
+    // Cressman records (and culls) half stages; IDW whole ones
+    constexpr int SUB = (WMODE == kCressman) ? kSubStages : 1;
+    constexpr int KS = kKSteps / SUB;
     double* dst = args.wfrag + (size_t)blockIdx.x * args.n_stages * kWStageDoubles + threadIdx.x;
-    int* list = args.stage_list + (size_t)blockIdx.x * args.n_stages;
+    int* list = args.stage_list + (size_t)blockIdx.x * args.n_stages * kSubStages;
     double wsum[4] = {0.0, 0.0, 0.0, 0.0};
     double wmx = 0.0;
     if (threadIdx.x == 0) s_n_active = 0;
@@ -271,33 +285,38 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
         for (int i = threadIdx.x; i < ns * kKT; i += kThreads) s_st[i] = args.st_xy[st0 * kKT + i];
         __syncthreads();
         for (int sl = 0; sl < ns; sl++) {
-            if (WMODE == kCressman && args.stage_box != nullptr) {
-                // every station of the stage farther than R from every cell of the tile (box-to-box
-                // distance, with a safety margin): all weights are exactly 0 -> nothing to do
-                const double4 b = args.stage_box[st0 + sl];
-                const double gx = fmax(0.0, fmax(b.x - bx1, bx0 - b.z));
-                const double gy = fmax(0.0, fmax(b.y - by1, by0 - b.w));
-                if (gx * gx + gy * gy > args.wp.a * (1.0 + 1e-9)) continue;
-            }
-            double w[kKSteps];
-            bool any = false;
-            // independent reciprocal chains overlap; fixed summation order per k-step residue
 #pragma unroll
-            for (int kk = 0; kk < kKSteps; kk++) {
-                const double2 s = s_st[sl * kKT + kk * 4 + q];
-                const double dx = cxy.x - s.x, dy = cxy.y - s.y;
-                w[kk] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp);
-                wsum[kk & 3] += w[kk];
-                wmx = fmax(wmx, w[kk]);
-                any |= (w[kk] != 0.0);
-            }
-            // a stage whose 64 x kKT weights are all zero (Cressman: every station beyond R) is not
-            // stored and will be skipped by the contraction
-            if (__syncthreads_or(any)) {
-                double* d = dst + (size_t)(st0 + sl) * kWStageDoubles;
+            for (int h = 0; h < SUB; h++) {
+                const int sub = (st0 + sl) * SUB + h;
+                if (WMODE == kCressman && args.stage_box != nullptr) {
+                    // every station of the (half) stage farther than R from every cell of the tile
+                    // (box-to-box distance, with a safety margin): all weights are exactly 0
+                    const double4 b = args.stage_box[sub];
+                    const double gx = fmax(0.0, fmax(b.x - bx1, bx0 - b.z));
+                    const double gy = fmax(0.0, fmax(b.y - by1, by0 - b.w));
+                    if (gx * gx + gy * gy > args.wp.a * (1.0 + 1e-9)) continue;
+                }
+                double w[KS];
+                bool any = false;
+                // independent reciprocal chains overlap; fixed summation order per k-step residue
 #pragma unroll
-                for (int kk = 0; kk < kKSteps; kk++) __stcs(d + kk * kThreads, w[kk]);
-                if (threadIdx.x == 0) list[s_n_active++] = st0 + sl;
+                for (int kk = 0; kk < KS; kk++) {
+                    const int ks = h * KS + kk;      // k-step inside the 16-station stage
+                    const double2 s = s_st[sl * kKT + ks * 4 + q];
+                    const double dx = cxy.x - s.x, dy = cxy.y - s.y;
+                    w[kk] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp);
+                    wsum[ks & 3] += w[kk];
+                    wmx = fmax(wmx, w[kk]);
+                    any |= (w[kk] != 0.0);
+                }
+                // a (half) stage whose 64 x 4*KS weights are all zero (Cressman: every station beyond R) is
+                // not stored and will be skipped by the contraction
+                if (__syncthreads_or(any)) {
+                    double* d = dst + (size_t)(st0 + sl) * kWStageDoubles + (size_t)h * KS * kThreads;
+#pragma unroll
+                    for (int kk = 0; kk < KS; kk++) __stcs(d + kk * kThreads, w[kk]);
+                    if (threadIdx.x == 0) list[s_n_active++] = sub;
+                }
             }
         }
     }
@@ -325,11 +344,13 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
 // grid.x = n_cell_tiles * n_tiles, date tile fastest: CTAs that run together share the A tile
 // through L2 and the whole B operand (tens of MB) stays L2-resident.
 // ---------------------------------------------------------------------------------------------
-template <int NP, bool MASKED, bool DENOM_IN_OUT = false>
+//   KSTEPS : k-steps per pipeline stage: kKSteps (16 stations), or kCressmanKSteps (8) for Cressman's finer lists
+template <int NP, bool MASKED, bool DENOM_IN_OUT = false, int KSTEPS = kKSteps>
 __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArgs args) {
     static_assert(!(MASKED && DENOM_IN_OUT), "the denominator comes either from the mask GEMM or from the output buffer");
-    using L = SmemLayout<MASKED>;
+    using L = SmemLayout<MASKED, KSTEPS>;
     constexpr int kStages = L::kStages;
+    constexpr int kStageW = KSTEPS * kThreads;   // doubles of the A cache per (half) stage
     static_assert(NP >= 1 && NP <= (MASKED ? 4 : 8), "64 accumulator registers per thread");
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -346,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
     const int col0 = tile_t0 % kGran;   // 0, or 64 for the second masked half of a granule
     // the tile's list of stages with any non-zero weight (all of them for IDW; for Cressman only
     // the stations near the tile: the rest of the dense product is exactly zero and is skipped)
-    const int* list = args.stage_list + (size_t)ct_local * args.n_stages;
+    const int* list = args.stage_list + (size_t)ct_local * args.n_stages * kSubStages;
     const int n_stages = args.n_active[ct_local];
 
     if (threadIdx.x == 0) {
@@ -360,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int it = 0; it < kStages && it < n_stages; it++)
-            produce_stage<MASKED>(args, smem, full_bar, it, __ldg(list + it), gran0);
+            produce_stage<MASKED, KSTEPS>(args, smem, full_bar, it, __ldg(list + it), gran0);
     }
 
     const int q = lane & 3;   // k index inside a k-step (A column / B row)
@@ -382,11 +403,11 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
         }
     }
 
-    double w_cur[kKSteps];
+    double w_cur[KSTEPS];
     if (n_stages > 0) {
-        const double* w0 = wsrc + (size_t)__ldg(list) * kWStageDoubles;
+        const double* w0 = wsrc + (size_t)__ldg(list) * kStageW;
 #pragma unroll
-        for (int kk = 0; kk < kKSteps; kk++) w_cur[kk] = __ldg(w0 + kk * kThreads);
+        for (int kk = 0; kk < KSTEPS; kk++) w_cur[kk] = __ldg(w0 + kk * kThreads);
     }
 
     for (int it = 0; it < n_stages; it++) {
@@ -395,19 +416,19 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
         const double* zs = reinterpret_cast<const double*>(smem + slot * L::kStageBytes);
 
         // A fragments of the next stage: in flight underneath this stage's DMMAs
-        double w_next[kKSteps];
+        double w_next[KSTEPS];
         {
             const int itn = (it + 1 < n_stages) ? it + 1 : it;
-            const double* wn = wsrc + (size_t)__ldg(list + itn) * kWStageDoubles;
+            const double* wn = wsrc + (size_t)__ldg(list + itn) * kStageW;
 #pragma unroll
-            for (int kk = 0; kk < kKSteps; kk++) w_next[kk] = __ldg(wn + kk * kThreads);
+            for (int kk = 0; kk < KSTEPS; kk++) w_next[kk] = __ldg(wn + kk * kThreads);
         }
         mbar_wait(&full_bar[slot], j & 1);
 #pragma unroll
-        for (int kk = 0; kk < kKSteps; kk++) {
+        for (int kk = 0; kk < KSTEPS; kk++) {
             const double a = w_cur[kk];
             const double* zrow = zs + (kk * 4 + q) * kGranLd + col0 + 2 * r;
-            const double* mrow = zrow + kBlkDoubles;  // mask granule block follows the z0 block
+            const double* mrow = zrow + L::kPartDoubles;  // the mask part follows the z0 part
 #pragma unroll
             for (int i = 0; i < NP; i++) {
                 // one LDS.128 = the thread's B elements of two adjacent column groups -> two DMMAs
@@ -429,11 +450,11 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
                 release_cnt[slot] = 0;
                 __threadfence_block();
                 if (it + kStages < n_stages)
-                    produce_stage<MASKED>(args, smem, full_bar, it + kStages, __ldg(list + it + kStages), gran0);
+                    produce_stage<MASKED, KSTEPS>(args, smem, full_bar, it + kStages, __ldg(list + it + kStages), gran0);
             }
         }
 #pragma unroll
-        for (int kk = 0; kk < kKSteps; kk++) w_cur[kk] = w_next[kk];
+        for (int kk = 0; kk < KSTEPS; kk++) w_cur[kk] = w_next[kk];
     }
 
     // ===== epilogue: normalise, NA rule, per-date early-outs, store =====
