@@ -351,7 +351,13 @@ def run_ours(a):
         "unit": "TFLOP/s",
         "frac": achieved / peaks["dmma_tflops"],
         "traffic": None,
-        "kernel": "ipr::contract_kernel<8,%s> (FP64 DMMA.8x8x4, 2 CTAs/SM)" % ("true" if a.workload == "idw_masked" else "false"),
+        "kernel": {
+            "idw": "ipr::contract_kernel<8,false,false,4> (FP64 DMMA.8x8x4, 2 CTAs/SM)",
+            "cressman": "ipr::contract_kernel<8,false,false,2> (FP64 DMMA.8x8x4, 2 CTAs/SM, 8-station half stages)",
+            "idw_masked": ("ipr::contract_kernel<8,false,true,4> (numerator, FP64 DMMA) + ipr::denom_imma_kernel (mask GEMM, IMMA)"
+                           if os.environ.get("IPR_MASK_INT8", "1") != "0" else
+                           "ipr::contract_kernel<4,true,false,4> (numerator + mask accumulators, FP64 DMMA.8x8x4)"),
+        }[a.workload],
         "peak_source": "profiles/fp64_peaks.json: DMMA m8n8k4 probe measured on this pool's B200 "
                        "(MEASURED_PEAKS.json has no FP64 entry); cuBLAS DGEMM 8192^3 = %.1f TFLOP/s"
                        % peaks["cublas_dgemm_tflops_burst"],
