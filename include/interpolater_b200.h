@@ -17,6 +17,12 @@
  *
  * Every entry point returns 0 on success or a negative IPR_E* code, and writes a message to
  * `err` (if non-NULL).  There is NO CPU fallback: without a usable sm_100 device the calls fail.
+ * No C++ exception leaves the library (host allocation failures come back as IPR_ENOMEM), and the
+ * library never calls back into the host language.
+ *
+ * Threading: the one-shot calls may be issued concurrently from several threads; a plan must be
+ * used by one thread at a time.  Device work buffers, streams and pinned staging slots are cached
+ * process-wide between calls (ipr_release_cached_memory() returns the device memory).
  */
 #ifndef INTERPOLATER_B200_H
 #define INTERPOLATER_B200_H
