@@ -4,6 +4,7 @@
 #include "interpolater_b200.h"   // include/ (build adds -I)
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <map>
 #include <memory>
@@ -89,11 +90,10 @@ DevicePool& pool() {
     return p;
 }
 size_t pool_limit_bytes() {
-    static size_t v = 0;
-    if (!v) {
+    static const size_t v = [] {
         const char* e = getenv("IPR_POOL_MAX_GB");
-        v = (size_t)(e ? atoll(e) : 64) << 30;
-    }
+        return (size_t)(e ? atoll(e) : 64) << 30;
+    }();
     return v;
 }
 
@@ -291,7 +291,7 @@ void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, TileSets& ts)
 template <int NP, bool MASKED, int KSTEPS = kKSteps>
 int launch_contract(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles, char* err, size_t errlen) {
     using L = SmemLayout<MASKED, KSTEPS>;
-    static bool configured[64] = {false};
+    static std::atomic<bool> configured[64];   // zero-initialised; racing first calls both set the attribute
     auto kern = contract_kernel<NP, MASKED, false, KSTEPS>;
     if (!configured[p->device & 63]) {
         IPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -411,7 +411,7 @@ int ensure_wcache(ipr_plan* p, bool need_wq, char* err, size_t errlen) {
 template <int NP>
 int launch_contract_denom(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles, char* err, size_t errlen) {
     using L = SmemLayout<false>;
-    static bool configured[64] = {false};
+    static std::atomic<bool> configured[64];   // zero-initialised; racing first calls both set the attribute
     auto kern = contract_kernel<NP, false, true>;
     if (!configured[p->device & 63]) {
         IPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -470,7 +470,7 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
     }
     IPR_CUDA(cudaMemsetAsync(p->d_fb_count, 0, sizeof(int), p->stream));
     {
-        static bool configured[64] = {false};
+        static std::atomic<bool> configured[64];   // zero-initialised; racing first calls both set the attribute
         if (!configured[p->device & 63]) {
             IPR_CUDA(cudaFuncSetAttribute(denom_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenomSmemBytes));
             configured[p->device & 63] = true;

@@ -485,6 +485,37 @@ def test_multi_device_scheduler_on_one_gpu(n_dates):
     assert_parity(one, ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="sharded idw")
 
 
+def test_concurrent_one_shot_calls_from_two_threads():
+    """include/interpolater_b200.h: the one-shot entry points may be called concurrently (the pools
+    behind them are process-wide); each thread gets the result of its own inputs."""
+    import threading
+
+    cases = [synthetic.synthetic_case(60, 50, 70, 200, na_frac=0.1, seed=31),
+             synthetic.synthetic_case(45, 70, 90, 150, na_frac=0.3, plant_zero_dist=2, seed=32)]
+    want = [engine.idw_grid(*c) for c in cases] + [engine.cressman_grid(*cases[0], np.array([8e3, 30e3]))]
+    got = [None] * 3
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                if i < 2:
+                    got[i] = engine.idw_grid(*cases[i])
+                else:
+                    got[i] = engine.cressman_grid(*cases[0], np.array([8e3, 30e3]))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w, equal_nan=True)
+
+
 def test_error_paths_report_messages():
     lib = _native.load()
     cx, cy, sx, sy, obs = synthetic.synthetic_case(4, 4, 5, 3)
