@@ -132,3 +132,75 @@ def test_extract_cells_edges():
     g = ref.grid_from_extent(0.0, 40.0, 0.0, 30.0, 10.0)
     cells = ref.extract_cells(g, [5.0, 40.0, 0.0, 41.0, 15.0], [25.0, 0.0, 30.0, 5.0, -1.0])
     assert cells == [0, 11, 0, -1, -1]
+
+
+# ----------------------------------------------------------------------------- oracle properties
+# Size-independent properties of the algorithm itself (the GPU suite checks the same ones at full
+# size): they guard the restatement against slips that the scalar twin, written from the same
+# reading of the reference, could share.
+def _case(seed, n_cells=40, n_st=9, n_dates=7, na=0.25):
+    rng = np.random.default_rng(seed)
+    cx, cy = rng.random(n_cells) * 5e4 + 7e5, rng.random(n_cells) * 5e4 + 9.6e6
+    sx, sy = rng.random(n_st) * 5e4 + 7e5, rng.random(n_st) * 5e4 + 9.6e6
+    obs = np.round(rng.gamma(0.8, 8.0, (n_dates, n_st)), 1)
+    obs[rng.random(obs.shape) < na] = np.nan
+    obs[:, 0] = np.where(np.isnan(obs[:, 0]), 1.5, obs[:, 0])       # no all-NA date
+    return cx, cy, sx, sy, obs
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_idw_oracle_properties(seed):
+    cx, cy, sx, sy, obs = _case(seed)
+    out = ref.idw_reference(cx, cy, sx, sy, obs, 2.0)
+    lo, hi = np.nanmin(obs, axis=1), np.nanmax(obs, axis=1)
+    assert np.all(out >= lo[None, :] - 1e-9) and np.all(out <= hi[None, :] + 1e-9)   # convex combination
+    # a field that is constant over the available stations is reproduced
+    const = np.where(np.isnan(obs), np.nan, np.arange(1, obs.shape[0] + 1)[:, None] * 2.5)
+    oc = ref.idw_reference(cx, cy, sx, sy, const, 2.0)
+    assert np.allclose(oc, (np.arange(1, obs.shape[0] + 1) * 2.5)[None, :], rtol=1e-12)
+    # linear in the observations for a fixed availability pattern
+    mix = ref.idw_reference(cx, cy, sx, sy, 2.0 * obs + 3.0 * const, 2.0)
+    assert np.allclose(mix, 2.0 * out + 3.0 * oc, rtol=1e-11, atol=1e-11)
+    # station order only permutes the summation
+    perm = np.random.default_rng(seed + 100).permutation(sx.size)
+    op = ref.idw_reference(cx, cy, sx[perm], sy[perm], obs[:, perm], 2.0)
+    assert np.allclose(op, out, rtol=1e-12)
+    # a rigid shift of all coordinates changes nothing beyond rounding of the differences
+    os_ = ref.idw_reference(cx + 1024.0, cy - 2048.0, sx + 1024.0, sy - 2048.0, obs, 2.0)
+    assert np.allclose(os_, out, rtol=1e-9)
+    # p -> large: the nearest available station dominates
+    o50 = ref.idw_reference(cx, cy, sx, sy, obs, 60.0)
+    d = np.hypot(cx[:, None] - sx[None, :], cy[:, None] - sy[None, :])
+    for t in range(obs.shape[0]):
+        avail = ~np.isnan(obs[t])
+        dn = np.where(avail[None, :], d, np.inf)
+        srt = np.sort(dn, axis=1)
+        clear = srt[:, 1] > 1.5 * srt[:, 0]        # second-nearest at least 50 % farther: weight ratio < 3e-11
+        near = np.argmin(dn, axis=1)
+        assert np.allclose(o50[clear, t], obs[t, near[clear]], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_cressman_oracle_properties(seed):
+    cx, cy, sx, sy, obs = _case(seed, na=0.0)
+    radii = np.array([6e3, 15e3, 80e3])
+    outs = ref.cressman_reference(cx, cy, sx, sy, obs, radii)
+    d = np.hypot(cx[:, None] - sx[None, :], cy[:, None] - sy[None, :])
+    for R, out in zip(radii, outs):
+        none_in_range = ~(d < R).any(axis=1)       # w > 0 only for d < R (d == R gives (R^2-d^2) = 0)
+        assert np.array_equal(np.isnan(out[:, 0]), none_in_range)
+        assert np.array_equal(np.isnan(out), np.repeat(none_in_range[:, None], obs.shape[0], axis=1))
+        ok = ~none_in_range
+        assert np.all(out[ok] >= obs.min(axis=1)[None, :].repeat(ok.sum(), 0) - 1e-9)
+        assert np.all(out[ok] <= obs.max(axis=1)[None, :].repeat(ok.sum(), 0) + 1e-9)
+    # radii are independent passes: one radius alone gives the same stack
+    solo = ref.cressman_reference(cx, cy, sx, sy, obs, radii[1:2])[0]
+    assert np.array_equal(solo, outs[1], equal_nan=True)
+    # an unavailable station still counts in the denominator (R/Cressman.R:315): dropping its value
+    # lowers the estimate by exactly its share
+    o2 = obs.copy()
+    o2[:, 3] = np.nan
+    with_na = ref.cressman_reference(cx, cy, sx, sy, o2, radii[2:3])[0]
+    w = np.where(d > radii[2], 0.0, (radii[2] ** 2 - d * d) / (radii[2] ** 2 + d * d))
+    share = w[:, 3:4] * obs[:, 3][None, :] / w.sum(axis=1)[:, None]
+    assert np.allclose(with_na, outs[2] - share, rtol=1e-11, atol=1e-11)
