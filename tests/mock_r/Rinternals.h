@@ -1,6 +1,6 @@
 /* Minimal stand-in for R's C API, ONLY so that r-package/src/r_shim.c can be syntax- and
  * type-checked where R is not installed (tests/test_r_shim_syntax.py).  Declarations follow
- * R >= 4.4's Rinternals.h; nothing here is linked or executed. */
+ * R >= 4.4's Rinternals.h.  mock_runtime.c implements them for tests/test_r_shim_runtime.py. */
 #ifndef MOCK_RINTERNALS_H
 #define MOCK_RINTERNALS_H
 #include <stddef.h>

@@ -1,0 +1,83 @@
+"""The .Call shim (r-package/src/r_shim.c), linked against the real C-ABI library and EXECUTED under
+a minimal mock of R's runtime (tests/mock_r/mock_runtime.c plays R: builds the SEXPs, looks the
+routine up in the registration table, calls it, catches `error()`).
+
+CPU: without a device the core fails and the shim must turn that into an R error, with the protect
+stack balanced.  GPU: the arrays that come back through the shim match the oracle."""
+import os
+import shutil
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_parity
+from interpolater_b200 import _native, synthetic
+
+pytestmark = pytest.mark.skipif(shutil.which("gcc") is None, reason="gcc not available")
+
+
+@pytest.fixture(scope="module")
+def driver(tmp_path_factory):
+    libdir = os.path.dirname(os.path.abspath(_native.LIB_PATH))
+    exe = str(tmp_path_factory.mktemp("shim") / "shim_driver")
+    cmd = ["gcc", "-std=c11", "-O1", "-Wall", "-Wextra", "-Wno-cast-function-type",
+           "-I", os.path.join(ROOT, "tests", "mock_r"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "mock_r", "mock_runtime.c"), os.path.join(ROOT, "r-package", "src", "r_shim.c"),
+           "-L", libdir, "-linterpolater_b200", "-Wl,-rpath," + libdir, "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def _write_case(path, mode, cx, cy, sx, sy, obs, last):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<5q", mode, cx.size, sx.size, obs.shape[0], len(last)))
+        for a in (cx, cy, sx, sy, np.asfortranarray(obs).ravel(order="F"), np.asarray(last, np.float64)):
+            f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+
+
+def _run(driver, tmp_path, mode, case, last):
+    cx, cy, sx, sy, obs = case
+    src, dst = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    _write_case(src, mode, cx, cy, sx, sy, obs, last)
+    res = subprocess.run([driver, src, dst], capture_output=True, text=True, timeout=300)
+    out = np.fromfile(dst, dtype=np.float64) if res.returncode == 0 else None
+    return res, out
+
+
+def _has_gpu():
+    return _native.load().ipr_device_count() > 0
+
+
+def test_shim_raises_an_r_error_without_a_device(driver, tmp_path):
+    if _has_gpu():
+        pytest.skip("a device is present: covered by the GPU test")
+    case = synthetic.synthetic_case(6, 5, 7, 9, na_frac=0.1)
+    for mode, last in ((0, [2.0]), (1, [5e3, 2e4])):
+        res, out = _run(driver, tmp_path, mode, case, last)
+        assert res.returncode == 3, (res.returncode, res.stderr)      # error() was raised, nothing crashed
+        assert out is None and "R error: interpolater_b200 (code -" in res.stderr
+
+
+@pytest.mark.gpu
+def test_shim_end_to_end_matches_oracle(driver, tmp_path):
+    from oracle import reference_port as ref
+
+    case = synthetic.synthetic_case(37, 23, 41, 150, na_frac=0.15, plant_zero_dist=2, all_na_dates=(4,),
+                                    all_zero_dates=(9,), seed=77)
+    cx, cy, sx, sy, obs = case
+    res, out = _run(driver, tmp_path, 0, case, [2.0])
+    assert res.returncode == 0, res.stderr
+    got = out.reshape(obs.shape[0], cx.size).T                        # column-major n_cells x n_dates
+    assert_parity(got, ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="IDW through the .Call shim")
+    na_bits = np.frombuffer(got[np.isnan(got)].tobytes(), dtype=np.uint64)
+    assert na_bits.size and np.all(na_bits == 0x7FF00000000007A2)      # is.na() and printing as NA in R
+    radii = [4e3, 1.5e4]
+    res, out = _run(driver, tmp_path, 1, case, radii)
+    assert res.returncode == 0, res.stderr
+    stacks = out.reshape(len(radii), obs.shape[0], cx.size)
+    want = ref.cressman_reference(cx, cy, sx, sy, obs, np.asarray(radii))
+    for ri in range(len(radii)):
+        assert_parity(stacks[ri].T, want[ri], label=f"Cressman R={radii[ri]:.0f} through the .Call shim")
