@@ -2,7 +2,6 @@
 the same seeded inputs, against the committed golden fixtures, and — at BASELINE.json's full size —
 through size-independent properties.  Tolerance (SURVEY §8c / north_star): 1e-9 relative in double,
 NA positions exact, exact-zero layers bit-exact."""
-import ctypes as C
 import os
 
 import numpy as np

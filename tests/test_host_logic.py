@@ -2,7 +2,6 @@
 IDW()/Cressman()) against the oracle and against the reference's own test expectations
 (tests/testthat/test-IDW.R, test-Cressman.R: error strings, layer counts, file creation)."""
 import math
-import os
 
 import numpy as np
 import pandas as pd

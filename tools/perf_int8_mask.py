@@ -1,7 +1,7 @@
 """cfg 5 (20 % NA): FP64 masked GEMM vs error-free int8 mask contraction (IPR_MASK_INT8)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from interpolater_b200 import engine, synthetic
 cx, cy, sx, sy, obs = synthetic.synthetic_case(1000, 1000, 2000, 3650, na_frac=0.2)
 C, D = cx.size, 3650

@@ -1,7 +1,7 @@
 """cfg-3 shape with a small NA fraction: sparse denominator correction vs masked GEMM."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from interpolater_b200 import engine, synthetic
 na = float(sys.argv[1]) if len(sys.argv) > 1 else 0.01
 cx, cy, sx, sy, obs = synthetic.synthetic_case(1000, 1000, 2000, 3650, na_frac=na)
