@@ -249,7 +249,7 @@ struct ipr_plan {
     bool int8_mask = false;
     int n_kblocks = 0;
     double* d_wmax = nullptr;
-    uint4* d_wq = nullptr;
+    unsigned char* d_wq = nullptr;   // digit planes, UMMA B-operand image per (32-cell group, k-block)
     unsigned char* d_mask8 = nullptr;
     int2* d_fb_list = nullptr;
     int* d_fb_count = nullptr;
@@ -363,6 +363,11 @@ int ensure_weights(ipr_plan* p, int mode, const WeightParams& wp, int tile0, int
     return IPR_OK;
 }
 
+// bytes of the digit planes for `tiles` 64-cell tiles: 7 bytes per (cell, padded station)
+size_t wq_bytes(const ipr_plan* p, long long tiles) {
+    return (size_t)tiles * (kCellsPerCta / kUCells) * p->n_kblocks * kUBBytes;
+}
+
 // Lazily sizes the A-operand cache: the whole grid if it fits in half of the free device memory
 // (IPR_WCACHE_MB overrides), otherwise the largest chunk of cell tiles that does.
 int ensure_wcache(ipr_plan* p, bool need_wq, char* err, size_t errlen) {
@@ -370,7 +375,7 @@ int ensure_wcache(ipr_plan* p, bool need_wq, char* err, size_t errlen) {
         // digit planes wanted later than the weights (NA data arrived after an NA-free run): same chunk
         // size; if they do not fit, this plan keeps both GEMMs on the FP64 pipe
         if (need_wq && !p->d_wq &&
-            dev_malloc(&p->d_wq, sizeof(uint4) * (size_t)p->w_chunk_tiles * p->n_kblocks * kQTileKbU4) != cudaSuccess) {
+            dev_malloc(&p->d_wq, wq_bytes(p, p->w_chunk_tiles)) != cudaSuccess) {
             cudaGetLastError();
             p->d_wq = nullptr;
             p->int8_mask = false;
@@ -392,7 +397,7 @@ int ensure_wcache(ipr_plan* p, bool need_wq, char* err, size_t errlen) {
     if (e == cudaSuccess) e = dev_malloc(&p->d_stage_list, sizeof(int) * (size_t)tiles * p->n_stages * kSubStages);
     if (e == cudaSuccess) e = dev_malloc(&p->d_n_active, sizeof(int) * (size_t)tiles);
     if (e == cudaSuccess && need_wq)
-        e = dev_malloc(&p->d_wq, sizeof(uint4) * (size_t)tiles * p->n_kblocks * kQTileKbU4);
+        e = dev_malloc(&p->d_wq, wq_bytes(p, tiles));
     if (e != cudaSuccess) {  // leave the plan without a cache, so that a later call starts over
         dev_free(p->d_wfrag);
         dev_free(p->d_stage_list);
@@ -429,11 +434,16 @@ int launch_contract_denom(ipr_plan* p, ContractArgs& a, const std::vector<int>& 
 }
 
 // Masked granules of [t0, t1) for the current cell-tile chunk: digit planes of the weights (cached
-// like the weights), integer mask contraction into the output buffer, numerator GEMM dividing by
-// it, direct re-evaluation of the listed ill-scaled pairs.
+// like the weights), integer mask contraction (tcgen05 kind::i8) into the output buffer, numerator GEMM
+// dividing by it, direct re-evaluation of the listed ill-scaled pairs.  If that list overflows (weights so
+// peaked that a missing nearest station leaves a denominator below 2^-10 of the row scale on millions of
+// pairs, e.g. large p with many NA), the launch group falls back by itself to the FP64 masked GEMM: the
+// same tiles are launched again with both accumulators on the DMMA pipe, and those CTAs exit at once
+// unless the device-side overflow flag is set — no host round trip, no failed call.
 int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs& a, const TileSets& ts, int t0, int t1,
                     char* err, size_t errlen) {
     const double key = (mode == kIdwEvenP) ? (double)wp.n : wp.a;
+    const int n_groups = a.n_cell_tiles * (kCellsPerCta / kUCells);
     if (!(p->wq_mode == mode && p->wq_param == key && p->wq_tile0 == a.cell_tile0)) {
         WeightArgs w{};
         w.cell_xy = p->d_cell;
@@ -443,12 +453,12 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
         w.n_stages = p->n_stages;
         w.wp = wp;
         if (mode == kIdwP2)
-            slice_weights_kernel<kIdwP2><<<a.n_cell_tiles, 256, 0, p->stream>>>(w, p->d_wmax, p->d_wq, p->n_kblocks);
+            slice_weights_kernel<kIdwP2><<<n_groups, 256, 0, p->stream>>>(w, p->d_wmax, p->d_wq, p->n_kblocks, p->n_st);
         else if (mode == kIdwEvenP)
-            slice_weights_kernel<kIdwEvenP><<<a.n_cell_tiles, 256, 0, p->stream>>>(w, p->d_wmax, p->d_wq, p->n_kblocks);
+            slice_weights_kernel<kIdwEvenP><<<n_groups, 256, 0, p->stream>>>(w, p->d_wmax, p->d_wq, p->n_kblocks, p->n_st);
         else
-            slice_weights_kernel<kIdwGenericP><<<a.n_cell_tiles, 256, 0, p->stream>>>(w, p->d_wmax, p->d_wq,
-                                                                                     p->n_kblocks);
+            slice_weights_kernel<kIdwGenericP><<<n_groups, 256, 0, p->stream>>>(w, p->d_wmax, p->d_wq, p->n_kblocks,
+                                                                                p->n_st);
         IPR_CUDA(cudaGetLastError());
         p->launches++;
         p->wq_mode = mode;
@@ -457,6 +467,7 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
     }
     // granules (128 dates) covered by the masked half tiles, with the width needed inside the window
     std::vector<int> gran[9];
+    std::vector<int> all_gran;
     {
         std::vector<int> starts;
         for (int np : {4, 2})
@@ -467,14 +478,16 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
             const int used = std::min(b + kGran, t1) - b;
             gran[used > 96 ? 8 : used > 64 ? 6 : used > 32 ? 4 : 2].push_back(b);
         }
+        all_gran = starts;
     }
-    IPR_CUDA(cudaMemsetAsync(p->d_fb_count, 0, sizeof(int), p->stream));
-    {
-        static std::atomic<bool> configured[64];   // zero-initialised; racing first calls both set the attribute
-        if (!configured[p->device & 63]) {
-            IPR_CUDA(cudaFuncSetAttribute(denom_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenomSmemBytes));
-            configured[p->device & 63] = true;
-        }
+    // [0] list length, [1] overflow flag of this launch group
+    IPR_CUDA(cudaMemsetAsync(p->d_fb_count, 0, 2 * sizeof(int), p->stream));
+    static std::atomic<int> n_sm[64];   // zero-initialised; racing first calls write the same value
+    if (!n_sm[p->device & 63]) {
+        IPR_CUDA(cudaFuncSetAttribute(denom_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
+        int v = 0;
+        IPR_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, p->device));
+        n_sm[p->device & 63] = v;
     }
     DenomArgs d{};
     d.wq = p->d_wq;
@@ -484,8 +497,8 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
     d.out = a.out;
     d.ld_out = a.ld_out;
     d.n_cells = p->n_cells;
-    d.cell_tile0 = a.cell_tile0;
-    d.n_cell_tiles = a.n_cell_tiles;
+    d.cell_group0 = a.cell_tile0 * (kCellsPerCta / kUCells);
+    d.n_cell_groups = n_groups;
     d.n_kblocks = p->n_kblocks;
     d.t_lo = t0;
     d.t_hi = t1;
@@ -493,16 +506,16 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
     d.fb_count = p->d_fb_count;
     d.fb_cap = p->fb_cap;
     int rc;
-    for (int np : {8, 6, 4, 2}) {
-        const std::vector<int>& tiles = gran[np];
-        for (size_t i0 = 0; i0 < tiles.size(); i0 += kMaxTilesPerLaunch) {
-            const int n = (int)std::min<size_t>(kMaxTilesPerLaunch, tiles.size() - i0);
-            d.tiles.n = n;
-            for (int i = 0; i < n; i++) d.tiles.t0[i] = tiles[i0 + i];
-            denom_imma_kernel<<<(unsigned)((long long)a.n_cell_tiles * n), kThreads, kDenomSmemBytes, p->stream>>>(d);
-            IPR_CUDA(cudaGetLastError());
-            p->launches++;
-        }
+    for (size_t i0 = 0; i0 < all_gran.size(); i0 += kMaxTilesPerLaunch) {
+        const int n = (int)std::min<size_t>(kMaxTilesPerLaunch, all_gran.size() - i0);
+        d.tiles.n = n;
+        for (int i = 0; i < n; i++) d.tiles.t0[i] = all_gran[i0 + i];
+        // persistent: one CTA per SM walks the (cell group, granule) tiles
+        const long long tiles = (long long)n_groups * n;
+        const unsigned grid = (unsigned)std::min<long long>(tiles, n_sm[p->device & 63]);
+        denom_umma_kernel<<<grid, kUThreads, kUSmemBytes, p->stream>>>(d);
+        IPR_CUDA(cudaGetLastError());
+        p->launches++;
     }
     if (!gran[8].empty() && (rc = launch_contract_denom<8>(p, a, gran[8], err, errlen))) return rc;
     if (!gran[6].empty() && (rc = launch_contract_denom<6>(p, a, gran[6], err, errlen))) return rc;
@@ -520,6 +533,11 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
         IPR_CUDA(cudaGetLastError());
         p->launches++;
     }
+    // fallback: both GEMMs on the FP64 pipe for the same tiles, executed only if the list overflowed
+    a.run_if = p->d_fb_count + 1;
+    if (!ts.m[4].empty() && (rc = launch_contract<4, true>(p, a, ts.m[4], err, errlen))) return rc;
+    if (!ts.m[2].empty() && (rc = launch_contract<2, true>(p, a, ts.m[2], err, errlen))) return rc;
+    a.run_if = nullptr;
     return IPR_OK;
 }
 
@@ -688,10 +706,9 @@ int prepare_obs(ipr_plan* p, char* err, size_t errlen) {
         p->launches++;
     }
     if (p->int8_mask) {
-        const long long total = (long long)p->n_gran * p->n_kblocks * 16 * 32;
+        const long long total = (long long)p->n_gran * p->n_kblocks * 2 * kGran;
         prep_mask8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(
-            p->d_obs, p->n_dates, p->n_dates, p->n_st, p->d_perm, reinterpret_cast<uint2*>(p->d_mask8), p->n_kblocks,
-            p->n_gran);
+            p->d_obs, p->n_dates, p->n_dates, p->n_st, p->d_perm, p->d_mask8, p->n_kblocks, p->n_gran);
         IPR_CUDA(cudaGetLastError());
         p->launches++;
     }
@@ -816,7 +833,7 @@ static int plan_create_impl(ipr_plan** plan, int device, const double* cell_x, c
     IPR_CUDA(cudaEventCreate(&p->ev1));
     IPR_CUDA(dev_malloc(&p->d_cell, sizeof(double2) * p->c_pad));
     // padded so that both the 16-station stages and the 32-station integer k-blocks stay in bounds
-    const size_t st_alloc = (size_t)std::max<long long>(p->s_pad + kKT, round_up((p->s_pad + kQKb - 1) / kQKb, kM8Kbs) * kQKb);
+    const size_t st_alloc = (size_t)std::max<long long>(p->s_pad + kKT, round_up((p->s_pad + kQKb - 1) / kQKb, kQKbPad) * kQKb);
     IPR_CUDA(dev_malloc(&p->d_st, sizeof(double2) * st_alloc));
     IPR_CUDA(dev_malloc(&p->d_obs, sizeof(double) * (size_t)n_dates * n_st));
     IPR_CUDA(dev_malloc(&p->d_z0, sizeof(double) * p->z_doubles));
@@ -830,13 +847,14 @@ static int plan_create_impl(ipr_plan** plan, int device, const double* cell_x, c
     IPR_CUDA(dev_malloc(&p->d_pairs, sizeof(int2) * p->pair_capacity));
     IPR_CUDA(dev_malloc(&p->d_wsum, sizeof(double) * p->c_pad));
     IPR_CUDA(dev_malloc(&p->d_wmax, sizeof(double) * p->c_pad));
-    p->n_kblocks = (int)round_up((p->s_pad + kQKb - 1) / kQKb, kM8Kbs);   // padded: whole pipeline stages
+    p->n_kblocks = (int)round_up((p->s_pad + kQKb - 1) / kQKb, kQKbPad);   // padded: whole pipeline stages
     // default on; the error bound of the digit planes is derived for at most 2^16 stations
     p->int8_mask = !(getenv("IPR_MASK_INT8") && atoi(getenv("IPR_MASK_INT8")) == 0) && n_st <= 65536;
     if (p->int8_mask) {
-        IPR_CUDA(dev_malloc(&p->d_mask8, (size_t)p->n_gran * p->n_kblocks * kM8BlkBytes));
+        IPR_CUDA(dev_malloc(&p->d_mask8, (size_t)p->n_gran * p->n_kblocks * kUABytes));
+        if (const char* e = getenv("IPR_FB_CAP")) p->fb_cap = std::max(1, atoi(e));   // tests: force the overflow path
         IPR_CUDA(dev_malloc(&p->d_fb_list, sizeof(int2) * (size_t)p->fb_cap));
-        IPR_CUDA(dev_malloc(&p->d_fb_count, sizeof(int) * 2));   // [0] list length, [1] sticky overflow flag
+        IPR_CUDA(dev_malloc(&p->d_fb_count, sizeof(int) * 2));   // [0] list length, [1] overflow flag of the launch group
         IPR_CUDA(cudaMemsetAsync(p->d_fb_count, 0, sizeof(int) * 2, p->stream));
     }
     IPR_CUDA(dev_malloc(&p->d_perm, sizeof(int) * n_st));
@@ -1121,12 +1139,6 @@ int ipr_plan_sync(ipr_plan* p) {
     if (!p) return IPR_EINVAL;
     cudaSetDevice(p->device);
     if (cudaStreamSynchronize(p->stream) != cudaSuccess) return IPR_ECUDA;
-    if (p->d_fb_count) {
-        // sticky flag of the int8 mask path: more ill-scaled (cell, date) pairs than its list holds
-        int ovf = 0;
-        if (cudaMemcpy(&ovf, p->d_fb_count + 1, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return IPR_ECUDA;
-        if (ovf) return IPR_EUNSUPPORTED;
-    }
     return IPR_OK;
 }
 int ipr_plan_timer_start(ipr_plan* p) {
@@ -1462,9 +1474,7 @@ int run_device_block(const HostJob& job, int device, long long c0, long long c1,
     }
     tr.mark("all chunks submitted");
     if ((rc = ipr_plan_sync(plan))) {
-        set_err(err, errlen, rc == IPR_EUNSUPPORTED
-                                 ? "too many ill-scaled (cell, date) pairs for the int8 mask path; set IPR_MASK_INT8=0"
-                                 : "stream synchronisation failed");
+        set_err(err, errlen, "stream synchronisation failed");
         return rc;
     }
     tr.mark("compute stream drained");

@@ -94,6 +94,8 @@ struct ContractArgs {
     int cell_tile0, n_cell_tiles;
     int n_stages;
     int t_lo, t_hi;           // store window [t_lo, t_hi)
+    const int* run_if;        // nullptr, or a device flag: the launch is a no-op unless it is non-zero (fallback
+                              // of the int8 mask path, decided on the device)
     TileList tiles;
 };
 
@@ -358,6 +360,7 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
     // no warp ever blocks on "slot empty"
     int* release_cnt = reinterpret_cast<int*>(full_bar + kStages);
 
+    if (args.run_if != nullptr && *args.run_if == 0) return;   // uniform for the whole grid
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tile_idx = blockIdx.x % args.tiles.n;
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
             const double numer = acc[f][c];
             double* optr = &args.out[(long long)(t - args.t_lo) * args.ld_out + cell];
             // DENOM_IN_OUT: the per-date denominator was left in the output buffer by
-            // denom_imma_kernel (error-free int8 mask contraction) and is replaced by the result
+            // denom_umma_kernel (error-free int8 mask contraction) and is replaced by the result
             const double denom = MASKED ? accm[f][c] : (DENOM_IN_OUT ? *optr : wsum);
             // date-independent denominator: one true division per thread (inv_wsum), then multiplies
             double v = (MASKED || DENOM_IN_OUT) ? numer / denom : numer * inv_wsum;
@@ -675,81 +678,88 @@ __global__ void idw_sparse_na_fix_kernel(const double2* __restrict__ cell_xy, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// Error-free int8 contraction of the availability mask (IDW with many NA).
+// Error-free int8 contraction of the availability mask (IDW with many NA) on the 5th-generation
+// tensor cores: tcgen05.mma kind::i8, accumulators in TMEM.
 //   denom[c,t] = sum_s w(c,s) m(s,t),  m in {0,1}
 // is the second GEMM of the masked path.  m is exact in 8 bits, so the weights are cut into
-// kQSlices 8-bit digits below a per-cell power-of-two scale, w = 2^e_c * sum_i d_i 256^-(i+1), each
-// digit plane is contracted with the mask on the INTEGER tensor pipe (mma.sync m16n8k32 u8 x u8 ->
-// s32: the sums, at most 2000*255, are exact) and the planes are recombined in FP64.  IMMA runs 31x
-// faster than DMMA on B200 (profiles/r01_fp64_probe.log; same tensor pipe, the two do not overlap), so
-// the seven plane GEMMs cost a fraction of the FP64 GEMM they replace.  Truncation below 2^(e_c-56) bounds the error
-// by S * 2^-56 of the scale; (cell, date) pairs whose denominator is so small against the scale
-// (< 2^-10: the cell's dominant station is missing) that this could exceed 1e-9 of it are listed and
-// recomputed directly by idw_direct_fix_kernel.
+// kQSlices 8-bit digits below a per-cell power-of-two scale, w = 2^e_c * sum_i d_i 256^-(i+1); each
+// digit plane contracted with the byte mask gives exact int32 sums (at most S * 255 < 2^31 for the
+// S <= 65 536 stations the path is enabled for) and the planes are recombined exactly in two int64
+// limbs and one FP64 rounding.  Truncation below 2^(e_c-56) bounds the error by S * 2^-56 of the
+// scale; (cell, date) pairs whose denominator is so small against the scale (< 2^-10: the cell's
+// dominant station is missing) that this could exceed 1e-9 of it are listed and recomputed directly
+// by idw_direct_fix_kernel (a list that overflows switches the launch group to the FP64 masked GEMM).
+//
+// One MMA computes D[128 dates x 224] += A[128 dates x 32 stations] * B[224 x 32 stations]^T with
+// A = the byte mask of a granule and B = the seven digit planes of 32 cells (N = plane * 32 + cell):
+// every plane reuses the same mask tile, which is read ONCE.  Measured on B200 (tools/umma_i8_probe.cu):
+// 112 cycles per M128 N224 K32 MMA from shared memory = 4.54 POP/s (N <= 128 is bound at 80 cycles by
+// the shared-memory read of A), against 1.14 POP/s for the legacy mma.sync IMMA path of round 1.
+// Both operands live in HBM as the canonical no-swizzle K-major shared-memory image (core matrix =
+// 8 rows x 16 bytes contiguous; SBO = 256 B between 8-row groups, LBO = 128 B between the two 16-byte
+// K halves), so a pipeline stage is filled by two plain 1-D bulk copies and needs no tensor map.
 // ---------------------------------------------------------------------------------------------
 constexpr int kQSlices = 7;
-constexpr int kQKb = 32;                                   // stations per integer k-block
-constexpr int kQTileKbU4 = kQSlices * 4 * 32;              // uint4 per (64-cell tile, k-block)
-constexpr int kM8BlkBytes = 16 * 32 * 8;                   // mask bytes per (granule, k-block), B-fragment order
-constexpr int kM8Kbs = 4;                                  // k-blocks per pipeline stage (one 16 KB bulk copy)
-constexpr int kM8Stages = 3;
+constexpr int kQKb = 32;                                   // stations per integer k-block (K of kind::i8)
+constexpr int kQKbPad = 4;                                 // n_kblocks is padded to a multiple of this
+constexpr int kUCells = 32;                                // cells per MMA tile
+constexpr int kUN = kQSlices * kUCells;                    // 224 = N of one MMA
+constexpr int kUABytes = kGran * kQKb;                     // 4096: mask image per (granule, k-block)
+constexpr int kUBBytes = kUN * kQKb;                       // 7168: digit image per (32-cell group, k-block)
+constexpr int kUKbs = 2;                                   // k-blocks per pipeline stage
+constexpr int kUStages = 8;
+constexpr int kUStageBytes = kUKbs * (kUABytes + kUBBytes);   // 22 528
+constexpr int kUThreads = 192;                             // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int kUTmemCols = 512;                            // two accumulator buffers of 224 columns (at 0 and 256)
+constexpr int kUSmemBytes = kUStages * kUStageBytes + (2 * kUStages + 4) * 8 + 16;
 constexpr double kQDirectBelow = 0x1p-10;                  // denominators below this share of the scale are re-evaluated in FP64
+static_assert(kQKbPad % kUKbs == 0, "whole pipeline stages");
 
 struct DenomArgs {
-    const uint4* wq;           // [n_cell_tiles][kQSlices][n_kblocks][4 m-frags][32 lanes]
-    const unsigned char* mask8;  // [n_gran][n_kblocks][kM8BlkBytes]
-    const double* wmax;        // [c_pad]
+    const unsigned char* wq;     // [n_cell_groups][n_kblocks][kUBBytes] digit planes (chunk-relative)
+    const unsigned char* mask8;  // [n_gran][n_kblocks][kUABytes]
+    const double* wmax;          // [c_pad]
     const uint8_t* date_flag;
     double* out;
     long long ld_out, n_cells;
-    int cell_tile0, n_cell_tiles, n_kblocks;
+    int cell_group0, n_cell_groups, n_kblocks;   // 32-cell groups; cell_group0 is absolute
     int t_lo, t_hi;
-    int2* fb_list;             // (cell, date) pairs to recompute directly
+    int2* fb_list;               // (cell, date) pairs to recompute directly
     int* fb_count;
     int fb_cap;
-    TileList tiles;            // granule start dates
+    TileList tiles;              // granule start dates
 };
-
-__device__ __forceinline__ void imma_u8(int (&c)[4], const uint4& a, const uint2& b) {
-    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
-        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y));
-}
 
 // power-of-two scale of a cell's weights: 2^e > wmax (0 when the row has no weight at all)
 __device__ __forceinline__ int row_exponent(double wmax) {
     return (wmax > 0.0 && isfinite(wmax)) ? ilogb(wmax) + 1 : 0;
 }
 
-// digit planes of the weights in IMMA A-fragment order.  One CTA per 64-cell tile; threads
-// (half, m-frag, lane): half selects the parity of the k-blocks the thread works on.
+// byte offset of (row, k) inside one k-block image of the canonical K-major layout
+__host__ __device__ constexpr int umma_kmajor_offset(int row, int k) {
+    return (row >> 3) * 256 + (k >> 4) * 128 + (row & 7) * 16 + (k & 15);
+}
+
+// digit planes of the weights as the B-operand image.  One CTA per 32-cell group; thread = (cell,
+// part), the parts stride over the 16-station halves of the k-blocks (a 16-byte row of a core matrix).
 template <int WMODE>
 __global__ void __launch_bounds__(256) slice_weights_kernel(const WeightArgs args, const double* __restrict__ wmax,
-                                                            uint4* __restrict__ wq, int n_kblocks) {
-    const int half = threadIdx.x >> 7;
-    const int mf = (threadIdx.x >> 5) & 3;
-    const int lane = threadIdx.x & 31;
-    const int g = lane >> 2, q = lane & 3;
-    const long long cell_a = (long long)(args.cell_tile0 + blockIdx.x) * kCellsPerCta + mf * 16 + g;
-    const long long cell_b = cell_a + 8;
-    const double2 ca = args.cell_xy[cell_a], cb = args.cell_xy[cell_b];
-    const double sa = scalbn(1.0, -row_exponent(wmax[cell_a]));
-    const double sb = scalbn(1.0, -row_exponent(wmax[cell_b]));
-    uint4* dst = wq + (size_t)blockIdx.x * n_kblocks * kQTileKbU4 + mf * 32 + lane;
-    for (int kb = half; kb < n_kblocks; kb += 2) {
-        double x[16];  // a0: row a, k = 4q..4q+3 | a1: row b, same k | a2: row a, k+16 | a3: row b, k+16
+                                                            unsigned char* __restrict__ wq, int n_kblocks, int n_st) {
+    const int cl = threadIdx.x & 31;
+    const int part = threadIdx.x >> 5;
+    const long long cell = ((long long)args.cell_tile0 * (kCellsPerCta / kUCells) + blockIdx.x) * kUCells + cl;
+    const double2 c = args.cell_xy[cell];
+    const double sc = scalbn(1.0, -row_exponent(wmax[cell]));
+    unsigned char* dst = wq + (size_t)blockIdx.x * n_kblocks * kUBBytes + umma_kmajor_offset(cl, 0);
+    for (int hk = part; hk < 2 * n_kblocks; hk += 8) {
+        double x[16];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const double2 s0 = __ldg(&args.st_xy[kb * kQKb + q * 4 + i]);
-            const double2 s1 = __ldg(&args.st_xy[kb * kQKb + q * 4 + i + 16]);
-            double dx = ca.x - s0.x, dy = ca.y - s0.y;
-            x[i] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp) * sa;
-            dx = cb.x - s0.x, dy = cb.y - s0.y;
-            x[4 + i] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp) * sb;
-            dx = ca.x - s1.x, dy = ca.y - s1.y;
-            x[8 + i] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp) * sa;
-            dx = cb.x - s1.x, dy = cb.y - s1.y;
-            x[12 + i] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp) * sb;
+        for (int i = 0; i < 16; i++) {
+            const int s = hk * 16 + i;
+            const double2 st = __ldg(&args.st_xy[s]);   // uniform across the warp: broadcast
+            const double dx = c.x - st.x, dy = c.y - st.y;
+            const double w = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp) * sc;
+            x[i] = (s < n_st) ? w : 0.0;                // padded stations carry no weight
         }
 #pragma unroll
         for (int sl = 0; sl < kQSlices; sl++) {
@@ -761,163 +771,224 @@ __global__ void __launch_bounds__(256) slice_weights_kernel(const WeightArgs arg
                 x[j] -= (double)d;                   // exact
                 r[j >> 2] |= (unsigned)d << (8 * (j & 3));
             }
-            dst[((size_t)sl * n_kblocks + kb) * 128] = make_uint4(r[0], r[1], r[2], r[3]);
+            // row n = sl * 32 + cl of the k-block image, K half hk & 1
+            *reinterpret_cast<uint4*>(dst + (size_t)(hk >> 1) * kUBBytes + sl * (kUCells / 8) * 256 + (hk & 1) * 128) =
+                make_uint4(r[0], r[1], r[2], r[3]);
         }
     }
 }
 
-// availability mask as bytes in IMMA B-fragment order (one thread = one lane's 8 bytes)
+// availability mask as bytes, A-operand image: one thread = 16 stations of one date (a core-matrix row)
 __global__ void prep_mask8_kernel(const double* __restrict__ obs, long long ld_obs, int n_dates, int n_st,
-                                  const int* __restrict__ perm, uint2* __restrict__ mask8, int n_kblocks,
+                                  const int* __restrict__ perm, unsigned char* __restrict__ mask8, int n_kblocks,
                                   int n_gran) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)n_gran * n_kblocks * 16 * 32;
+    const long long total = (long long)n_gran * n_kblocks * 2 * kGran;
     if (idx >= total) return;
-    const int lane = (int)(idx & 31);
-    const int j = (int)((idx >> 5) & 15);
-    const long long blk = idx >> 9;               // granule * n_kblocks + kb
+    const int tl = (int)(idx & (kGran - 1));      // date inside the granule: consecutive lanes, coalesced obs reads
+    const int h = (int)((idx >> 7) & 1);
+    const long long blk = idx >> 8;               // granule * n_kblocks + kb
     const int kb = (int)(blk % n_kblocks);
     const int gran = (int)(blk / n_kblocks);
-    const int t = gran * kGran + j * 8 + (lane >> 2);
-    unsigned b[2] = {0u, 0u};
+    const int t = gran * kGran + tl;
+    unsigned r[4] = {0u, 0u, 0u, 0u};
     if (t < n_dates) {
 #pragma unroll
-        for (int hh = 0; hh < 2; hh++)
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int k = kb * kQKb + (lane & 3) * 4 + i + 16 * hh;
-                if (k < n_st) {
-                    const double v = obs[(long long)perm[k] * ld_obs + t];
-                    if (v == v) b[hh] |= 1u << (8 * i);
-                }
+        for (int i = 0; i < 16; i++) {
+            const int k = kb * kQKb + h * 16 + i;
+            if (k < n_st) {
+                const double v = obs[(long long)perm[k] * ld_obs + t];
+                if (v == v) r[i >> 2] |= 1u << (8 * (i & 3));
             }
+        }
     }
-    mask8[idx] = make_uint2(b[0], b[1]);
+    *reinterpret_cast<uint4*>(mask8 + (size_t)blk * kUABytes + umma_kmajor_offset(tl, h * 16)) =
+        make_uint4(r[0], r[1], r[2], r[3]);
 }
 
-// denominators of one granule (128 dates) for a 64-cell tile: 8 warps = 2 (32 cells) x 4 (32 dates).
-// n_kblocks is a multiple of kM8Kbs (both operands are padded with zeros).
-__global__ void __launch_bounds__(kThreads, 2) denom_imma_kernel(const DenomArgs args) {
-    extern __shared__ __align__(128) unsigned char dsm[];
-    constexpr int kMaskBytes = kM8Kbs * kM8BlkBytes;       // 16 KB: mask bytes of 4 k-blocks
-    constexpr int kABytes = kM8Kbs * 4 * 32 * 16;          // 8 KB: one digit plane of the tile's weights
-    constexpr int kStageBytes = kMaskBytes + kABytes;
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(dsm + kM8Stages * kStageBytes);
-    int* s_release = reinterpret_cast<int*>(s_full + kM8Stages);
+// ---- tcgen05 helpers ----
+// shared-memory matrix descriptor: no swizzle, K-major, version 1 (Blackwell); offsets in 16-byte units
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+// instruction descriptor of kind::i8: D = s32, A = B = u8, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n) {
+    return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier when every MMA issued so far by this thread has completed (implies
+// tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Persistent kernel, one CTA per SM.  Tile = (32-cell group, 128-date granule), granule fastest so that
+// concurrently running CTAs share the group's digit planes through L2.  Warp 0 streams the operands
+// through an 8-deep mbarrier pipeline, one lane of warp 1 issues the MMAs into one of two TMEM
+// accumulator buffers, warps 2-5 (one per TMEM lane quarter) drain the other buffer: thread = date,
+// 7 planes x 32 cells of int32 sums -> 32 denominators.
+__global__ void __launch_bounds__(kUThreads, 1) denom_umma_kernel(const DenomArgs args) {
+    extern __shared__ __align__(1024) unsigned char usm[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(usm + kUStages * kUStageBytes);
+    uint64_t* empty_bar = full_bar + kUStages;
+    uint64_t* tfull_bar = empty_bar + kUStages;    // accumulator buffer ready for the epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;          // accumulator buffer drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wm = warp & 1, wn = warp >> 1;
-    const int g = lane >> 2, q = lane & 3;
-    const int tile_t0 = args.tiles.t0[blockIdx.x % args.tiles.n];
-    const int ct_local = blockIdx.x / args.tiles.n;
-    const int gran = tile_t0 / kGran;
-    const int nkb = args.n_kblocks;
-    const int nst = nkb / kM8Kbs;          // pipeline stages per digit plane
-    const int total = kQSlices * nst;      // the mask is re-streamed once per digit plane
+    const int nks = args.n_kblocks / kUKbs;
+    const int n_tiles = args.n_cell_groups * args.tiles.n;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kM8Stages; s++) {
-            mbar_init(&s_full[s], 1);
-            s_release[s] = 0;
+        for (int s = 0; s < kUStages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();
-    const uint4* wq_tile = args.wq + (size_t)ct_local * kQSlices * nkb * 128;
-    auto produce = [&](int pos) {
-        const int slot = pos % kM8Stages;
-        const int st = pos % nst, sl = pos / nst;   // stages inner, digit planes outer
-        unsigned char* stage = dsm + slot * kStageBytes;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&s_full[slot], kStageBytes);
-        bulk_g2s(stage, args.mask8 + ((size_t)gran * nkb + (size_t)st * kM8Kbs) * kM8BlkBytes, kMaskBytes, &s_full[slot]);
-        bulk_g2s(stage + kMaskBytes, wq_tile + ((size_t)sl * nkb + (size_t)st * kM8Kbs) * 128, kABytes, &s_full[slot]);
-    };
-    if (threadIdx.x == 0)
-        for (int pos = 0; pos < kM8Stages && pos < total; pos++) produce(pos);
-
-    int iacc[2][4][4];
-    double dacc[2][4][4];
-#pragma unroll
-    for (int m = 0; m < 2; m++)
-#pragma unroll
-        for (int n = 0; n < 4; n++)
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                iacc[m][n][e] = 0;
-                dacc[m][n][e] = 0.0;
-            }
-    double plane_scale = 1.0 / 256.0;
-    int st = 0;
-    for (int pos = 0; pos < total; pos++) {
-        const int slot = pos % kM8Stages;
-        const unsigned char* stage = dsm + slot * kStageBytes;
-        mbar_wait(&s_full[slot], (pos / kM8Stages) & 1);
-#pragma unroll
-        for (int u = 0; u < kM8Kbs; u++) {
-            // A fragments: m-frags 2wm, 2wm+1 ; B fragments: n-frags 4wn .. 4wn+3
-            const uint4* asrc = reinterpret_cast<const uint4*>(stage + kMaskBytes) + (u * 4 + 2 * wm) * 32 + lane;
-            const uint4 a0 = asrc[0], a1 = asrc[32];
-            const uint2* bsrc = reinterpret_cast<const uint2*>(stage + u * kM8BlkBytes) + (wn * 4) * 32 + lane;
-#pragma unroll
-            for (int n = 0; n < 4; n++) {
-                const uint2 b = bsrc[n * 32];
-                imma_u8(iacc[0][n], a0, b);
-                imma_u8(iacc[1][n], a1, b);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            if (atomicAdd(&s_release[slot], 1) == kConsumerWarps - 1) {
-                s_release[slot] = 0;
-                __threadfence_block();
-                if (pos + kM8Stages < total) produce(pos + kM8Stages);
-            }
-        }
-        if (++st == nst) {
-            // end of a digit plane: its exact integer sums enter the FP64 accumulators
-            st = 0;
-#pragma unroll
-            for (int m = 0; m < 2; m++)
-#pragma unroll
-                for (int n = 0; n < 4; n++)
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        dacc[m][n][e] = fma((double)iacc[m][n][e], plane_scale, dacc[m][n][e]);
-                        iacc[m][n][e] = 0;
-                    }
-            plane_scale *= 1.0 / 256.0;
-        }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kUTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_slot;
 
-    // store: c0,c1 -> row g, dates 2q, 2q+1 ; c2,c3 -> row g+8
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int cg = tile / args.tiles.n;
+                const int gran = args.tiles.t0[tile % args.tiles.n] / kGran;
+                const unsigned char* a_src = args.mask8 + (size_t)gran * args.n_kblocks * kUABytes;
+                const unsigned char* b_src = args.wq + (size_t)cg * args.n_kblocks * kUBBytes;
+                for (int ks = 0; ks < nks; ks++, it++) {
+                    const int s = it % kUStages;
+                    mbar_wait(&empty_bar[s], ((it / kUStages) & 1) ^ 1);
+                    unsigned char* stage = usm + s * kUStageBytes;
+                    mbar_expect_tx(&full_bar[s], kUStageBytes);
+                    bulk_g2s(stage, a_src + (size_t)ks * kUKbs * kUABytes, kUKbs * kUABytes, &full_bar[s]);
+                    bulk_g2s(stage + kUKbs * kUABytes, b_src + (size_t)ks * kUKbs * kUBBytes, kUKbs * kUBBytes,
+                             &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(kGran, kUN);
+            int it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tl++) {
+                const int buf = tl & 1;
+                mbar_wait(&tempty_bar[buf], ((tl >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tbase + (uint32_t)buf * 256u;
+                for (int ks = 0; ks < nks; ks++, it++) {
+                    const int s = it % kUStages;
+                    mbar_wait(&full_bar[s], (it / kUStages) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(usm + s * kUStageBytes);
 #pragma unroll
-    for (int m = 0; m < 2; m++) {
+                    for (int u = 0; u < kUKbs; u++)
+                        umma_i8(tacc, umma_smem_desc(sa + u * kUABytes), umma_smem_desc(sa + kUKbs * kUABytes + u * kUBBytes),
+                                idesc, (ks | u) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);   // the stage may be refilled once these MMAs have read it
+                }
+                umma_commit(&tfull_bar[buf]);
+            }
+        }
+    } else {
+        const int quarter = warp & 3;              // TMEM lanes [32 quarter, 32 quarter + 32) belong to this warp
+        const int row = quarter * 32 + lane;       // date inside the granule
+        const bool vec_ok = ((args.ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(args.out) & 15) == 0);
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tl++) {
+            const int buf = tl & 1;
+            const int cg = tile / args.tiles.n;
+            const int t = args.tiles.t0[tile % args.tiles.n] + row;
+            const long long cell0 = (long long)(args.cell_group0 + cg) * kUCells;
+            const double scale_l = scalbn(1.0, row_exponent(args.wmax[cell0 + lane]));   // lane <-> cell of the group
+            const bool t_ok = (t >= args.t_lo && t < args.t_hi);
+            const bool listable = t_ok && args.date_flag[t] == 0;
+            double* orow = args.out + (long long)(t_ok ? t - args.t_lo : 0) * args.ld_out + cell0;
+            mbar_wait(&tfull_bar[buf], (tl >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tacc = tbase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * 256u;
+#pragma unroll 1
+            for (int c8 = 0; c8 < kUCells / 8; c8++) {
+                uint32_t v[kQSlices][8];
 #pragma unroll
-        for (int hrow = 0; hrow < 2; hrow++) {
-            const long long cell = (long long)(args.cell_tile0 + ct_local) * kCellsPerCta + (2 * wm + m) * 16 + g + 8 * hrow;
-            if (cell >= args.n_cells) continue;
-            const double scale = scalbn(1.0, row_exponent(args.wmax[cell]));
+                for (int p = 0; p < kQSlices; p++) tmem_ld8(tacc + p * kUCells + c8 * 8, v[p]);
+                tmem_ld_wait();
+                if (c8 == kUCells / 8 - 1) {
+                    // last read of this accumulator buffer: hand it back to the MMA issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                }
+                double d[8];
 #pragma unroll
-            for (int n = 0; n < 4; n++)
+                for (int i = 0; i < 8; i++) {
+                    // exact recombination: plane sums < 2^24, limbs < 2^41 and < 2^49, one rounding at the end
+                    const long long hi = ((long long)v[0][i] << 16) + ((long long)v[1][i] << 8) + (long long)v[2][i];
+                    const long long lo = ((long long)v[3][i] << 24) + ((long long)v[4][i] << 16) +
+                                         ((long long)v[5][i] << 8) + (long long)v[6][i];
+                    d[i] = fma((double)hi, 0x1p-24, (double)lo * 0x1p-56);
+                }
 #pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int t = tile_t0 + (wn * 4 + n) * 8 + q * 2 + e;
-                    if (t < args.t_lo || t >= args.t_hi) continue;
-                    const double d = dacc[m][n][2 * hrow + e];
-                    args.out[(long long)(t - args.t_lo) * args.ld_out + cell] = d * scale;
+                for (int i = 0; i < 8; i++) {
+                    const double sc = __shfl_sync(0xffffffffu, scale_l, c8 * 8 + i);
+                    const long long cell = cell0 + c8 * 8 + i;
                     // truncation error < S * 2^-56 of the scale <= 2^-40 for S <= 2^16 stations (the host
                     // disables this path beyond): guaranteed below 1e-9 of d only while d >= 2^-10
-                    if (d < kQDirectBelow && args.date_flag[t] == 0) {
+                    if (d[i] < kQDirectBelow && listable && cell < args.n_cells) {
                         const int slot = atomicAdd(args.fb_count, 1);
                         if (slot < args.fb_cap) args.fb_list[slot] = make_int2((int)cell, t);
                     }
+                    d[i] *= sc;
                 }
+                if (t_ok) {
+                    double* o = orow + c8 * 8;
+                    if (vec_ok && cell0 + c8 * 8 + 8 <= args.n_cells) {
+#pragma unroll
+                        for (int i = 0; i < 8; i += 2) *reinterpret_cast<double2*>(o + i) = make_double2(d[i], d[i + 1]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            if (cell0 + c8 * 8 + i < args.n_cells) o[i] = d[i];
+                    }
+                }
+            }
         }
     }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(kUTmemCols) : "memory");
+    }
 }
-constexpr int kDenomSmemBytes = kM8Stages * (kM8Kbs * kM8BlkBytes + kM8Kbs * 4 * 32 * 16) + kM8Stages * 8 + kM8Stages * 4 + 16;
 
 // direct FP64 evaluation of listed (cell, date) pairs: one warp each
 template <int WMODE>
