@@ -348,6 +348,7 @@ int ensure_weights(ipr_plan* p, int mode, const WeightParams& wp, int tile0, int
     w.cell_tile0 = tile0;
     w.n_cell_tiles = n_tiles;
     w.n_stages = p->n_stages;
+    w.n_st = p->n_st;
     w.wp = wp;
     switch (mode) {
         case kIdwP2: weights_kernel<kIdwP2><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
@@ -1027,7 +1028,7 @@ static int plan_idw_impl(ipr_plan* p, double pw, int32_t t0, int32_t t1, double*
             const int te = std::min(t1, tb + 32768);
             dim3 grid((unsigned)((p->n_cells + threads - 1) / threads), (unsigned)(te - tb));
             double* o = d_out + (size_t)(tb - t0) * ld_out;
-#define IPR_FIX_ARGS p->d_cell, p->d_st, p->s_pad, p->d_wsum, p->n_cells, p->d_na_n, p->d_na_idx, p->d_date_mode, \
+#define IPR_FIX_ARGS p->d_cell, p->d_st, p->n_st, p->d_wsum, p->n_cells, p->d_na_n, p->d_na_idx, p->d_date_mode, \
                      p->d_flag, tb, te, wp, o, ld_out
             if (mode == kIdwP2) idw_sparse_na_fix_kernel<kIdwP2><<<grid, threads, 0, p->stream>>>(IPR_FIX_ARGS);
             else if (mode == kIdwEvenP) idw_sparse_na_fix_kernel<kIdwEvenP><<<grid, threads, 0, p->stream>>>(IPR_FIX_ARGS);

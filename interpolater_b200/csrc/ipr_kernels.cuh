@@ -113,6 +113,7 @@ struct WeightArgs {
     unsigned long long* active_total;  // cumulative count of active (cell tile, stage) blocks
     int cell_tile0, n_cell_tiles;
     int n_stages;
+    int n_st;                 // real stations; positions >= n_st are padding and carry exactly zero weight
     WeightParams wp;
 };
 
@@ -307,6 +308,8 @@ __global__ void __launch_bounds__(kThreads) weights_kernel(const WeightArgs args
                     const double2 s = s_st[sl * kKT + ks * 4 + q];
                     const double dx = cxy.x - s.x, dy = cxy.y - s.y;
                     w[kk] = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp);
+                    // padding is given weight 0 explicitly: at (1e150, 1e150) a small generic p would not underflow
+                    if ((st0 + sl) * kKT + ks * 4 + q >= args.n_st) w[kk] = 0.0;
                     wsum[ks & 3] += w[kk];
                     wmx = fmax(wmx, w[kk]);
                     any |= (w[kk] != 0.0);
@@ -630,7 +633,7 @@ __global__ void na_lists_kernel(const double* __restrict__ obs, long long ld_obs
 
 template <int WMODE>
 __global__ void idw_sparse_na_fix_kernel(const double2* __restrict__ cell_xy, const double2* __restrict__ st_xy,
-                                         int s_pad, const double* __restrict__ wsum, long long n_cells,
+                                         int n_st, const double* __restrict__ wsum, long long n_cells,
                                          const int* __restrict__ na_n, const int* __restrict__ na_idx,
                                          const uint8_t* __restrict__ date_mode, const uint8_t* __restrict__ date_flag,
                                          int t_lo, int t_hi, WeightParams wp, double* __restrict__ out,
@@ -661,7 +664,7 @@ __global__ void idw_sparse_na_fix_kernel(const double2* __restrict__ cell_xy, co
         // the weights of the available stations directly (rare: a missing station next to the cell)
         denom = 0.0;
         int k = 0;
-        for (int s = 0; s < s_pad; s++) {
+        for (int s = 0; s < n_st; s++) {
             if (k < n && s_idx[k] == s) {
                 k++;
                 continue;
@@ -752,25 +755,23 @@ __global__ void __launch_bounds__(256) slice_weights_kernel(const WeightArgs arg
     const double sc = scalbn(1.0, -row_exponent(wmax[cell]));
     unsigned char* dst = wq + (size_t)blockIdx.x * n_kblocks * kUBBytes + umma_kmajor_offset(cl, 0);
     for (int hk = part; hk < 2 * n_kblocks; hk += 8) {
-        double x[16];
+        // x = w / 2^e in [0, 1); its first 56 fraction bits, taken at once: x * 2^56 is exact and the
+        // conversion truncates, exactly like peeling seven base-256 digits one by one
+        unsigned long long u[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) {
             const int s = hk * 16 + i;
             const double2 st = __ldg(&args.st_xy[s]);   // uniform across the warp: broadcast
             const double dx = c.x - st.x, dy = c.y - st.y;
             const double w = weight_from_d2<WMODE>(fma(dy, dy, dx * dx), args.wp) * sc;
-            x[i] = (s < n_st) ? w : 0.0;                // padded stations carry no weight
+            u[i] = (s < n_st) ? __double2ull_rz(w * 0x1p56) : 0ull;   // padded stations carry no weight
         }
 #pragma unroll
         for (int sl = 0; sl < kQSlices; sl++) {
             unsigned r[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                x[j] *= 256.0;                       // exact (power of two)
-                const int d = (int)x[j];             // 0..255: x in [0, 1) before the scaling
-                x[j] -= (double)d;                   // exact
-                r[j >> 2] |= (unsigned)d << (8 * (j & 3));
-            }
+            for (int j = 0; j < 16; j++)
+                r[j >> 2] |= (unsigned)((u[j] >> (48 - 8 * sl)) & 255ull) << (8 * (j & 3));
             // row n = sl * 32 + cl of the k-block image, K half hk & 1
             *reinterpret_cast<uint4*>(dst + (size_t)(hk >> 1) * kUBBytes + sl * (kUCells / 8) * 256 + (hk & 1) * 128) =
                 make_uint4(r[0], r[1], r[2], r[3]);

@@ -251,7 +251,7 @@ def test_sparse_na_correction_matches_masked_gemm_and_oracle(monkeypatch):
 
 
 def test_int8_mask_contraction_matches_fp64_and_oracle(monkeypatch):
-    """Default path (IPR_MASK_INT8=0 disables): the availability-mask GEMM runs error-free on the integer tensor pipe (8-bit
+    """Default path (IPR_MASK_INT8=0 disables): the availability-mask GEMM runs error-free on the tcgen05 integer tensor path (8-bit
     digit planes of the weights); same 1e-9 bar against the oracle, and agreement with the FP64
     masked GEMM far below it, including a cell whose dominant station is missing (direct re-evaluation)."""
     cx, cy, sx, sy, obs = synthetic.synthetic_case(29, 23, 75, 300, na_frac=0.25, plant_zero_dist=2,
@@ -280,6 +280,30 @@ def test_int8_mask_contraction_matches_fp64_and_oracle(monkeypatch):
     plan.sync()
     assert_parity(o.cpu().numpy().T, want, label="int8 masked, windows")
     plan.close()
+
+
+def test_int8_mask_list_overflow_falls_back_to_fp64_gemm(monkeypatch):
+    """Peaked weights (p = 6) with many NA: far more (cell, date) pairs fall below 2^-10 of their row scale than
+    the direct-fix list holds (capacity forced to 8 here).  The launch group must switch to the FP64 masked GEMM
+    on the device by itself — same parity bar, no failed call (round-1 behaviour: IPR_EUNSUPPORTED)."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(40, 33, 60, 260, na_frac=0.3, plant_zero_dist=1, seed=77)
+    want = ref.idw_reference(cx, cy, sx, sy, obs, 6.0)
+    monkeypatch.setenv("IPR_FB_CAP", "8")
+    got = engine.idw_grid(cx, cy, sx, sy, obs, p=6.0)
+    assert_parity(got, want, label="int8 masked, overflowing fix list")
+    monkeypatch.delenv("IPR_FB_CAP")
+    assert_parity(engine.idw_grid(cx, cy, sx, sy, obs, p=6.0), want, label="int8 masked, roomy fix list")
+
+
+@pytest.mark.parametrize("p", [0.05, 0.1, 0.5])
+def test_idw_small_powers_padding_carries_no_weight(p):
+    """p < 1: a padded station at (1e150, 1e150) would weigh pow(2e300, -p/2) ~ 3e-8 (p = 0.05) if it were
+    left to underflow; station counts that are not multiples of 16 exercise the padding, NA-free, sparse-NA
+    and masked granules alike."""
+    for n_st, na in [(23, 0.0), (37, 0.01), (50, 0.3)]:
+        cx, cy, sx, sy, obs = synthetic.synthetic_case(19, 14, n_st, 140, na_frac=na, seed=n_st)
+        assert_parity(engine.idw_grid(cx, cy, sx, sy, obs, p=p), ref.idw_reference(cx, cy, sx, sy, obs, p),
+                      label=f"p={p} n_st={n_st} na={na}")
 
 
 def test_buffer_pool_release():
