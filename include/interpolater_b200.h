@@ -154,6 +154,21 @@ int64_t ipr_plan_launch_count(const ipr_plan* plan);
  * calls of ONE kind is meaningful; it lets a caller report executed vs dense-equivalent flops.
  * Synchronises the plan stream. */
 int ipr_plan_stage_blocks(ipr_plan* plan, uint64_t* executed, uint64_t* dense);
+/* Per-phase CUDA-event timing of what the plan launches, on the plan's own stream (off by default: an event
+ * pair costs a few microseconds per launch group).  ipr_plan_profile_read() synchronises the stream, adds the
+ * elapsed milliseconds of every finished span to ms[phase] (n >= IPR_N_PHASES doubles, zeroed by the call
+ * first) and forgets them.  This is how bench.py measures the dominant kernels live for the roofline. */
+#define IPR_PHASE_PREP 0       /* obs preparation: NA split, flags, NA lists, byte mask */
+#define IPR_PHASE_WEIGHTS 1    /* A operand generation (weights_kernel) */
+#define IPR_PHASE_CONTRACT 2   /* FP64 DMMA contraction (IDW: unmasked, numerator or masked GEMM) */
+#define IPR_PHASE_SLICE 3      /* digit planes of the weights (int8 mask path) */
+#define IPR_PHASE_MASK_GEMM 4  /* tcgen05 kind::i8 mask contraction */
+#define IPR_PHASE_FIXUP 5      /* zero-distance / sparse-NA / direct fixes and the conditional FP64 fallback */
+#define IPR_PHASE_POST 6       /* optional rounding / polygon mask pass */
+#define IPR_PHASE_RADIUS0 8    /* Cressman: the contraction of radius r is phase IPR_PHASE_RADIUS0 + r, r < 24 */
+#define IPR_N_PHASES 32
+int ipr_plan_profile(ipr_plan* plan, int enable);
+int ipr_plan_profile_read(ipr_plan* plan, double* ms, int n);
 /* number of (cell, station) pairs at exactly zero distance found for this geometry */
 int64_t ipr_plan_zero_pairs(const ipr_plan* plan);
 /* raw cudaStream_t of the plan (as void*) so a host framework can order its own work */

@@ -14,6 +14,10 @@ LIB_PATH = os.environ.get("IPR_LIB_OVERRIDE") or os.path.join(_HERE, "lib", "lib
 
 IPR_OK = 0
 ERRLEN = 512
+#: phases of ipr_plan_profile_read (include/interpolater_b200.h, IPR_PHASE_*)
+N_PHASES = 32
+PHASES = {"prep": 0, "weights": 1, "contract": 2, "slice": 3, "mask_gemm": 4, "fixup": 5, "post": 6}
+PHASE_RADIUS0 = 8
 
 #: every symbol include/interpolater_b200.h declares (checked by the CPU test-suite)
 EXPORTED_SYMBOLS = [
@@ -22,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "ipr_plan_create", "ipr_plan_destroy", "ipr_plan_set_obs", "ipr_plan_set_obs_device",
     "ipr_plan_idw", "ipr_plan_cressman", "ipr_plan_sync", "ipr_plan_reset_cache",
     "ipr_plan_timer_start", "ipr_plan_timer_stop", "ipr_plan_launch_count", "ipr_plan_zero_pairs",
-    "ipr_plan_stage_blocks",
+    "ipr_plan_stage_blocks", "ipr_plan_profile", "ipr_plan_profile_read",
     "ipr_plan_stream", "ipr_host_alloc", "ipr_host_free", "ipr_release_cached_memory",
 ]
 
@@ -96,6 +100,10 @@ def load() -> C.CDLL:
     lib.ipr_plan_launch_count.argtypes = [vp]
     lib.ipr_plan_stage_blocks.restype = C.c_int
     lib.ipr_plan_stage_blocks.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.ipr_plan_profile.restype = C.c_int
+    lib.ipr_plan_profile.argtypes = [vp, C.c_int]
+    lib.ipr_plan_profile_read.restype = C.c_int
+    lib.ipr_plan_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     lib.ipr_plan_zero_pairs.restype = C.c_int64
     lib.ipr_plan_zero_pairs.argtypes = [vp]
     lib.ipr_plan_stream.restype = vp

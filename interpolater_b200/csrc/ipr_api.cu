@@ -277,9 +277,42 @@ struct ipr_plan {
     int w_mode = -1;         // what the cache currently holds: weight mode, parameter, first tile
     double w_param = 0.0;
     int w_tile0 = -1;
+    // optional per-phase event timing (ipr_plan_profile)
+    bool prof_on = false;
+    int phase_radius = -1;   // Cressman: radius index of the contraction being launched
+    struct Span { int id; cudaEvent_t e0, e1; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> ev_pool;
 };
 
 namespace {
+
+// RAII span of one profiling phase on the plan stream (no-op unless ipr_plan_profile enabled it)
+struct PhaseScope {
+    ipr_plan* p;
+    cudaEvent_t e1 = nullptr;
+    PhaseScope(ipr_plan* plan, int id) : p(plan) {
+        if (!p->prof_on) return;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        for (auto& e : ev) {
+            if (!p->ev_pool.empty()) {
+                e = p->ev_pool.back();
+                p->ev_pool.pop_back();
+            } else if (cudaEventCreate(&e) != cudaSuccess) {
+                e = nullptr;
+            }
+        }
+        if (!ev[0] || !ev[1]) return;
+        cudaEventRecord(ev[0], p->stream);
+        e1 = ev[1];
+        p->spans.push_back({id, ev[0], ev[1]});
+    }
+    void finish() {
+        if (e1) cudaEventRecord(e1, p->stream);
+        e1 = nullptr;
+    }
+    ~PhaseScope() { finish(); }
+};
 
 // date tiles of one launch group: [MASKED][NP] -> start dates
 struct TileSets {
@@ -293,6 +326,8 @@ int launch_contract(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles,
     using L = SmemLayout<MASKED, KSTEPS>;
     static std::atomic<bool> configured[64];   // zero-initialised; racing first calls both set the attribute
     auto kern = contract_kernel<NP, MASKED, false, KSTEPS>;
+    PhaseScope ps(p, p->phase_radius >= 0 ? IPR_PHASE_RADIUS0 + std::min(p->phase_radius, 23)
+                                          : (a.run_if ? IPR_PHASE_FIXUP : IPR_PHASE_CONTRACT));
     if (!configured[p->device & 63]) {
         IPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         configured[p->device & 63] = true;
@@ -350,6 +385,7 @@ int ensure_weights(ipr_plan* p, int mode, const WeightParams& wp, int tile0, int
     w.n_stages = p->n_stages;
     w.n_st = p->n_st;
     w.wp = wp;
+    PhaseScope ps(p, IPR_PHASE_WEIGHTS);
     switch (mode) {
         case kIdwP2: weights_kernel<kIdwP2><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
         case kIdwEvenP: weights_kernel<kIdwEvenP><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
@@ -419,6 +455,7 @@ int launch_contract_denom(ipr_plan* p, ContractArgs& a, const std::vector<int>& 
     using L = SmemLayout<false>;
     static std::atomic<bool> configured[64];   // zero-initialised; racing first calls both set the attribute
     auto kern = contract_kernel<NP, false, true>;
+    PhaseScope ps(p, IPR_PHASE_CONTRACT);
     if (!configured[p->device & 63]) {
         IPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         configured[p->device & 63] = true;
@@ -453,6 +490,7 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
         w.n_cell_tiles = a.n_cell_tiles;
         w.n_stages = p->n_stages;
         w.wp = wp;
+        PhaseScope ps(p, IPR_PHASE_SLICE);
         if (mode == kIdwP2)
             slice_weights_kernel<kIdwP2><<<n_groups, 256, 0, p->stream>>>(w, p->d_wmax, p->d_wq, p->n_kblocks, p->n_st);
         else if (mode == kIdwEvenP)
@@ -508,6 +546,7 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
     d.fb_cap = p->fb_cap;
     int rc;
     for (size_t i0 = 0; i0 < all_gran.size(); i0 += kMaxTilesPerLaunch) {
+        PhaseScope ps(p, IPR_PHASE_MASK_GEMM);
         const int n = (int)std::min<size_t>(kMaxTilesPerLaunch, all_gran.size() - i0);
         d.tiles.n = n;
         for (int i = 0; i < n; i++) d.tiles.t0[i] = all_gran[i0 + i];
@@ -527,6 +566,7 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
 #define IPR_DF_ARGS p->d_fb_list, p->d_fb_count, p->fb_cap, p->d_fb_count + 1, p->d_cell, p->d_st, p->n_st, p->d_perm, \
                     p->d_obs, (long long)p->n_dates, wp, t0, a.out, a.ld_out
         const unsigned nb = 296;
+        PhaseScope ps(p, IPR_PHASE_FIXUP);
         if (mode == kIdwP2) idw_direct_fix_kernel<kIdwP2><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
         else if (mode == kIdwEvenP) idw_direct_fix_kernel<kIdwEvenP><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
         else idw_direct_fix_kernel<kIdwGenericP><<<nb, 256, 0, p->stream>>>(IPR_DF_ARGS);
@@ -620,6 +660,7 @@ void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, TileSets& ts)
 int run_post(ipr_plan* p, int t0, int t1, double* d_out, long long ld_out, char* err, size_t errlen) {
     if (p->post_round_mode == 0 && !p->d_cell_keep) return IPR_OK;
     dim3 grid((unsigned)((p->n_cells + 255) / 256), (unsigned)std::min(t1 - t0, 64));
+    PhaseScope ps(p, IPR_PHASE_POST);
     post_kernel<<<grid, 256, 0, p->stream>>>(d_out, ld_out, p->n_cells, t1 - t0, p->post_round_mode, p->post_p10,
                                              p->d_cell_keep);
     IPR_CUDA(cudaGetLastError());
@@ -695,6 +736,7 @@ int prepare_obs(ipr_plan* p, char* err, size_t errlen) {
     IPR_CUDA(cudaMemsetAsync(p->d_counters + 1, 0, sizeof(int), p->stream));
     dim3 block(32, 8);
     dim3 grid((unsigned)((p->n_dates + 31) / 32));
+    std::unique_ptr<PhaseScope> ps(new PhaseScope(p, IPR_PHASE_PREP));
     prep_obs_kernel<<<grid, block, 0, p->stream>>>(p->d_obs, p->n_dates, p->n_dates, p->n_st, p->d_perm, p->d_z0, p->d_mask,
                                                    p->n_stages, p->d_flag, p->d_has_na, p->d_counters + 1);
     IPR_CUDA(cudaGetLastError());
@@ -713,6 +755,7 @@ int prepare_obs(ipr_plan* p, char* err, size_t errlen) {
         IPR_CUDA(cudaGetLastError());
         p->launches++;
     }
+    ps.reset();
     int bad = 0;
     p->h_has_na.resize(p->n_dates);
     std::vector<int> na_n(p->n_dates);
@@ -962,6 +1005,11 @@ void ipr_plan_destroy(ipr_plan* p) {
     dev_free(p->d_stage_box);
     dev_free(p->d_cell_keep);
     dev_free(p->d_active_total);
+    for (auto& sp : p->spans) {
+        cudaEventDestroy(sp.e0);
+        cudaEventDestroy(sp.e1);
+    }
+    for (auto e : p->ev_pool) cudaEventDestroy(e);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) release_stream(p->stream);   // synchronised above
@@ -1022,6 +1070,7 @@ static int plan_idw_impl(ipr_plan* p, double pw, int32_t t0, int32_t t1, double*
     bool fix_here = false;
     if (p->any_sparse_fix)
         for (int t = t0; t < t1 && !fix_here; t++) fix_here = (p->h_date_mode[t] == 1);
+    PhaseScope ps_fix(p, IPR_PHASE_FIXUP);
     if (fix_here) {
         const int threads = 256;
         for (int tb = t0; tb < t1; tb += 32768) {
@@ -1045,6 +1094,7 @@ static int plan_idw_impl(ipr_plan* p, double pw, int32_t t0, int32_t t1, double*
         IPR_CUDA(cudaGetLastError());
         p->launches++;
     }
+    ps_fix.finish();
     return run_post(p, t0, t1, d_out, ld_out, err, errlen);
 }
 
@@ -1096,9 +1146,10 @@ static int plan_cressman_impl(ipr_plan* p, const double* radii_m, int32_t n_radi
     for (int ri = 0; ri < n_radii; ri++) {
         WeightParams wp{};
         wp.a = radii_m[ri] * radii_m[ri];
-        if ((rc = run_contraction(p, kCressman, wp, false, t0, t1, d_out + (size_t)ri * stack_stride, ld_out, err,
-                                  errlen)))
-            return rc;
+        p->phase_radius = ri;
+        rc = run_contraction(p, kCressman, wp, false, t0, t1, d_out + (size_t)ri * stack_stride, ld_out, err, errlen);
+        p->phase_radius = -1;
+        if (rc) return rc;
         if ((rc = run_post(p, t0, t1, d_out + (size_t)ri * stack_stride, ld_out, err, errlen))) return rc;
     }
     return IPR_OK;
@@ -1153,6 +1204,25 @@ int ipr_plan_timer_stop(ipr_plan* p, float* ms) {
     if (cudaEventRecord(p->ev1, p->stream) != cudaSuccess) return IPR_ECUDA;
     if (cudaEventSynchronize(p->ev1) != cudaSuccess) return IPR_ECUDA;
     return cudaEventElapsedTime(ms, p->ev0, p->ev1) == cudaSuccess ? IPR_OK : IPR_ECUDA;
+}
+int ipr_plan_profile(ipr_plan* p, int enable) {
+    if (!p) return IPR_EINVAL;
+    p->prof_on = enable != 0;
+    return IPR_OK;
+}
+int ipr_plan_profile_read(ipr_plan* p, double* ms, int n) {
+    if (!p || !ms || n < IPR_N_PHASES) return IPR_EINVAL;
+    cudaSetDevice(p->device);
+    if (cudaStreamSynchronize(p->stream) != cudaSuccess) return IPR_ECUDA;
+    for (int i = 0; i < n; i++) ms[i] = 0.0;
+    for (auto& sp : p->spans) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sp.e0, sp.e1) == cudaSuccess && sp.id >= 0 && sp.id < IPR_N_PHASES) ms[sp.id] += t;
+        p->ev_pool.push_back(sp.e0);
+        p->ev_pool.push_back(sp.e1);
+    }
+    p->spans.clear();
+    return IPR_OK;
 }
 int64_t ipr_plan_launch_count(const ipr_plan* p) { return p ? p->launches : 0; }
 int64_t ipr_plan_zero_pairs(const ipr_plan* p) { return p ? p->zero_pairs : 0; }

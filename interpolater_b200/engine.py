@@ -197,6 +197,20 @@ class Plan:
             raise _native.NativeError(-2, "stage block query failed")
         return int(ex.value), int(de.value)
 
+    def profile(self, enable=True):
+        """Switch the per-phase CUDA-event timing of the plan's launches on or off."""
+        self._lib.ipr_plan_profile(self._h, 1 if enable else 0)
+
+    def profile_read(self):
+        """Milliseconds per phase since the last read (synchronises): {"prep", "weights", "contract", "slice",
+        "mask_gemm", "fixup", "post", "radius": [ms per Cressman radius]}."""
+        ms = (C.c_double * _native.N_PHASES)()
+        if self._lib.ipr_plan_profile_read(self._h, ms, _native.N_PHASES) != 0:
+            raise _native.NativeError(-2, "profile read failed")
+        res = {k: float(ms[i]) for k, i in _native.PHASES.items()}
+        res["radius"] = [float(ms[i]) for i in range(_native.PHASE_RADIUS0, _native.N_PHASES)]
+        return res
+
     @property
     def zero_pairs(self) -> int:
         return int(self._lib.ipr_plan_zero_pairs(self._h))

@@ -215,6 +215,54 @@ def cressman_reference(cx, cy, sx, sy, obs, radii_m):
     return outs
 
 
+# --------------------------------------------------------------------------------------
+# Matrix form of the same two algorithms (Numer = W.Z0, Denom = W.M).  Used where the
+# literal per-date loop would take minutes (full-length records in bench.py's parity sample and the
+# full-size GPU tests); held to the literal restatement by tests/test_oracle.py.
+# --------------------------------------------------------------------------------------
+def idw_reference_matrix(cx, cy, sx, sy, obs, p=2.0):
+    """(n_cells, n_dates), equal to idw_reference up to the order of summation (BLAS GEMM instead of
+    a dgemv per date).  Early-outs R/IDW.R:294-302; cells with an exact zero distance (R/IDW.R:310-326)
+    are evaluated by the literal idw_one_date."""
+    obs = np.asarray(obs, np.float64)
+    dist_mat, w_base = idw_setup(cx, cy, sx, sy, p)
+    n_cells, n_dates = dist_mat.shape[0], obs.shape[0]
+    present = ~_is_na(obs)                                              # (n_dates, n_st)
+    z0 = np.where(present, obs, 0.0)
+    zero_rows = np.nonzero((dist_mat == 0).any(axis=1))[0]
+    w = w_base.copy()
+    w[zero_rows, :] = 0.0                                               # handled below
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        numer = w @ z0.T                                                # :329 / :336 for every date at once
+        denom = w @ present.astype(np.float64).T                        # :330 / :337
+        out = numer / denom                                             # :331 / :338
+    out[~np.isfinite(out) | (denom == 0)] = np.nan                      # :332 / :339
+    any_obs = present.any(axis=1)
+    all_small = np.array([np.all(np.abs(obs[t][present[t]]) < 1e-12) for t in range(n_dates)])
+    out[:, ~any_obs] = np.nan                                           # :299-301
+    out[:, any_obs & all_small] = 0.0                                   # :294-297
+    if zero_rows.size:
+        for t in range(n_dates):
+            out[zero_rows, t] = idw_one_date(dist_mat[zero_rows], w_base[zero_rows], obs[t])
+    return out
+
+
+def cressman_reference_matrix(cx, cy, sx, sy, obs, radii_m):
+    """List (one per radius) of (n_cells, n_dates): Numer = W_R.Z0 with NA obs skipped (R/Cressman.R:314),
+    denominator = row sums of W_R over ALL stations (:315), NA rule :317."""
+    obs = np.asarray(obs, np.float64)
+    z0 = np.where(_is_na(obs), 0.0, obs)
+    outs = []
+    for w in cressman_setup(cx, cy, sx, sy, radii_m):
+        numer = w @ z0.T
+        denom = _row_sums_na_rm(w)[:, None]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            o = numer / denom
+        o[~np.isfinite(o) | (denom == 0)] = np.nan
+        outs.append(o)
+    return outs
+
+
 def radius_names(radii_m):
     """R/Cressman.R:357  sprintf("%g km", R/1000)."""
     return ["%g km" % (r / 1000.0) for r in radii_m]

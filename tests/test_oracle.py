@@ -204,3 +204,24 @@ def test_cressman_oracle_properties(seed):
     w = np.where(d > radii[2], 0.0, (radii[2] ** 2 - d * d) / (radii[2] ** 2 + d * d))
     share = w[:, 3:4] * obs[:, 3][None, :] / w.sum(axis=1)[:, None]
     assert np.allclose(with_na, outs[2] - share, rtol=1e-11, atol=1e-11)
+
+
+def test_matrix_form_equals_literal_per_date_loop():
+    """oracle.idw_reference_matrix / cressman_reference_matrix (used for full-length records) against the
+    literal restatement: same NA pattern, same early-out layers, values equal to summation-order noise."""
+    from interpolater_b200 import synthetic
+
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(17, 12, 29, 75, na_frac=0.2, plant_zero_dist=3, all_na_dates=(4,),
+                                                   all_zero_dates=(9,), seed=5)
+    for p in (2.0, 3.5):
+        a, b = ref.idw_reference(cx, cy, sx, sy, obs, p), ref.idw_reference_matrix(cx, cy, sx, sy, obs, p)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        m = ~np.isnan(a)
+        assert np.allclose(a[m], b[m], rtol=1e-12, atol=0.0)
+        assert np.all(b[:, 9] == 0.0) and np.all(np.isnan(b[:, 4]))
+    radii = ref.cressman_radii_m([4, 9, 30])
+    for a, b in zip(ref.cressman_reference(cx, cy, sx, sy, obs, radii),
+                    ref.cressman_reference_matrix(cx, cy, sx, sy, obs, radii)):
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        m = ~np.isnan(a)
+        assert np.allclose(a[m], b[m], rtol=1e-12, atol=1e-300)
