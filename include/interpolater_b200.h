@@ -39,6 +39,7 @@ extern "C" {
 #define IPR_ECUDA (-2)    /* CUDA runtime error / no device */
 #define IPR_ENOMEM (-3)   /* device or pinned-host allocation failed */
 #define IPR_EUNSUPPORTED (-4)
+#define IPR_ECANCELLED (-5)  /* ipr_job_cancel() stopped the job */
 
 /* library version: major*10000 + minor*100 + patch */
 int ipr_version(void);
@@ -101,6 +102,46 @@ int ipr_cressman_post_f64(const double* cell_x, const double* cell_y, int64_t n_
                           int32_t round_mode, int32_t n_round, const uint8_t* cell_keep,
                           const int* devices, int n_devices,
                           double* out, char* err, size_t errlen);
+
+/* ---------------------------------------------------------------------------------------
+ * Asynchronous form of the one-shot calls, for a host language whose main thread must stay
+ * responsive: the reference wraps its per-date loop in a pbapply progress bar (R/IDW.R:350-352,
+ * R/Cressman.R:338-340) and R code is interruptible between dates.  ipr_job_start_* takes the
+ * arguments of ipr_idw_post_f64 / ipr_cressman_post_f64 (round_mode 0 and cell_keep NULL give the
+ * plain calls), starts the job on worker threads and returns at once; every array except radii_m must
+ * stay valid until ipr_job_finish().  The main thread then alternates
+ *     ipr_job_wait(job, 100, &done, &total)   -> 1 finished | 0 still running; progress in work items
+ *                                                (one 128-date chunk of one stack on one device, counted
+ *                                                when its layers have reached the host)
+ * with its own event handling (R: R_CheckUserInterrupt inside R_ToplevelExec, progress bar update), may
+ * call ipr_job_cancel() (the workers stop at the next chunk; what was written so far stays), and
+ * always ends with ipr_job_finish(), which joins, frees the job and returns its code
+ * (IPR_ECANCELLED after a cancel).  timeout_ms < 0 waits until the job has finished.
+ * ------------------------------------------------------------------------------------- */
+typedef struct ipr_job ipr_job;
+int ipr_job_start_idw(ipr_job** job,
+                      const double* cell_x, const double* cell_y, int64_t n_cells,
+                      const double* st_x, const double* st_y, int32_t n_st,
+                      const double* obs, int32_t n_dates, double p,
+                      int32_t round_mode, int32_t n_round, const uint8_t* cell_keep,
+                      const int* devices, int n_devices,
+                      double* out, char* err, size_t errlen);
+int ipr_job_start_cressman(ipr_job** job,
+                           const double* cell_x, const double* cell_y, int64_t n_cells,
+                           const double* st_x, const double* st_y, int32_t n_st,
+                           const double* obs, int32_t n_dates,
+                           const double* radii_m, int32_t n_radii,
+                           int32_t round_mode, int32_t n_round, const uint8_t* cell_keep,
+                           const int* devices, int n_devices,
+                           double* out, char* err, size_t errlen);
+int ipr_job_wait(ipr_job* job, int timeout_ms, int64_t* done, int64_t* total);
+void ipr_job_cancel(ipr_job* job);
+int ipr_job_finish(ipr_job* job, char* err, size_t errlen);
+
+/* The cell ranges the one-shot calls give to n_devices devices: bounds[0..n_devices], device g owns
+ * cells [bounds[g], bounds[g+1]) — contiguous, on 64-cell tile boundaries, equal to within one tile
+ * (no output element depends on another cell, so there is nothing to exchange). */
+void ipr_cell_split_bounds(int64_t n_cells, int n_devices, int64_t* bounds);
 
 /* ---------------------------------------------------------------------------------------
  * Device-resident plan API (used by the one-shot calls, the benchmark and the Python host

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IPR_LIB_OVERRIDE") or os.path.join(_HERE, "lib", "libinterpolater_b200.so")
 
 IPR_OK = 0
+IPR_ECANCELLED = -5
 ERRLEN = 512
 #: phases of ipr_plan_profile_read (include/interpolater_b200.h, IPR_PHASE_*)
 N_PHASES = 32
@@ -28,6 +29,8 @@ EXPORTED_SYMBOLS = [
     "ipr_plan_timer_start", "ipr_plan_timer_stop", "ipr_plan_launch_count", "ipr_plan_zero_pairs",
     "ipr_plan_stage_blocks", "ipr_plan_profile", "ipr_plan_profile_read",
     "ipr_plan_stream", "ipr_host_alloc", "ipr_host_free", "ipr_release_cached_memory",
+    "ipr_job_start_idw", "ipr_job_start_cressman", "ipr_job_wait", "ipr_job_cancel", "ipr_job_finish",
+    "ipr_cell_split_bounds",
 ]
 
 
@@ -114,6 +117,18 @@ def load() -> C.CDLL:
     lib.ipr_host_alloc.argtypes = [C.c_size_t]
     lib.ipr_host_free.restype = None
     lib.ipr_host_free.argtypes = [vp]
+    lib.ipr_job_start_idw.restype = C.c_int
+    lib.ipr_job_start_idw.argtypes = [C.POINTER(vp), *lib.ipr_idw_post_f64.argtypes]
+    lib.ipr_job_start_cressman.restype = C.c_int
+    lib.ipr_job_start_cressman.argtypes = [C.POINTER(vp), *lib.ipr_cressman_post_f64.argtypes]
+    lib.ipr_job_wait.restype = C.c_int
+    lib.ipr_job_wait.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.ipr_job_cancel.restype = None
+    lib.ipr_job_cancel.argtypes = [vp]
+    lib.ipr_job_finish.restype = C.c_int
+    lib.ipr_job_finish.argtypes = [vp, C.c_char_p, C.c_size_t]
+    lib.ipr_cell_split_bounds.restype = None
+    lib.ipr_cell_split_bounds.argtypes = [C.c_int64, C.c_int, C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 

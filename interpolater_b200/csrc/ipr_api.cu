@@ -21,6 +21,12 @@
 #include <thread>
 #include <vector>
 
+#include <pthread.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "ipr_kernels.cuh"
 
 using namespace ipr;
@@ -1087,9 +1093,9 @@ static int plan_idw_impl(ipr_plan* p, double pw, int32_t t0, int32_t t1, double*
             p->launches++;
         }
     }
-    if (p->n_fix > 0) {
-        dim3 grid((unsigned)((t1 - t0 + 127) / 128), (unsigned)p->n_fix);
-        idw_zero_fix_kernel<<<grid, 128, 0, p->stream>>>(p->d_fix_cell, p->d_fix_off, p->d_fix_st, p->n_fix, p->d_obs,
+    for (int f0 = 0; f0 < p->n_fix; f0 += 65535) {   // gridDim.y <= 65535
+        dim3 grid((unsigned)((t1 - t0 + 127) / 128), (unsigned)std::min(65535, p->n_fix - f0));
+        idw_zero_fix_kernel<<<grid, 128, 0, p->stream>>>(p->d_fix_cell, p->d_fix_off, p->d_fix_st, f0, p->n_fix, p->d_obs,
                                                          p->n_dates, p->d_flag, t0, t1, d_out, ld_out);
         IPR_CUDA(cudaGetLastError());
         p->launches++;
@@ -1250,9 +1256,115 @@ struct HostJob {
     bool out_pinned = false;  // caller's output is page-locked: D2H lands in it directly
     int round_mode = 0, n_round = 0;
     const uint8_t* cell_keep = nullptr;
+    int n_job_devices = 1;                        // devices sharing the host's cores / memory bandwidth in this job
+    // asynchronous jobs (ipr_job_*): cooperative cancellation and progress in work items (date chunks)
+    std::atomic<int>* cancel = nullptr;
+    std::atomic<long long>* done = nullptr;
 };
 
 constexpr int kRing = 3;
+
+// Work items of one device: (stack, date chunk), stack outermost so that the A-operand cache is generated
+// once per radius.  A chunk is one 128-date granule (1 GB per 10^6 cells): D2H starts after the first
+// granule and only the last granule's copy is left when the kernels finish.
+struct WorkItem { int stack, t0, t1; };
+std::vector<WorkItem> make_items(int n_stacks, int nd) {
+    std::vector<WorkItem> items;
+    for (int s = 0; s < n_stacks; s++)
+        for (int t = 0; t < nd; t += kGran) {
+            const int te = std::min(nd, t + kGran);
+            // the very first granule goes out as 32 + 96 dates: the copy engine starts after a quarter of
+            // a granule's kernels instead of a whole one (nothing else can overlap with that wait)
+            if (s == 0 && t == 0 && te > 32) {
+                items.push_back({s, 0, 32});
+                items.push_back({s, 32, te});
+            } else {
+                items.push_back({s, t, te});
+            }
+        }
+    return items;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host topology.  The D2H stream of a multi-GPU job is bound by the HOST side (round 1: 8 x 29 GB in
+// 2.6 s = 91 GB/s for the box against 57 GB/s for one GPU alone), so the threads that touch a device's
+// share of the output — its scheduler thread and the memcpy fan-out of the pageable path — run on the
+// CPUs sysfs reports as local to that device, and pinned memory they allocate is first touched there.
+// IPR_NUMA=0 disables all of it.  No libnuma dependency: sysfs + sched_setaffinity + set_mempolicy.
+// ---------------------------------------------------------------------------------------------
+bool numa_enabled() {
+    static const bool on = !(getenv("IPR_NUMA") && atoi(getenv("IPR_NUMA")) == 0);
+    return on;
+}
+
+std::vector<int> parse_cpulist(const char* s) {
+    std::vector<int> cpus;
+    while (*s) {
+        char* end = nullptr;
+        long lo = strtol(s, &end, 10);
+        if (end == s) break;
+        long hi = lo;
+        if (*end == '-') {
+            s = end + 1;
+            hi = strtol(s, &end, 10);
+        }
+        for (long c = lo; c <= hi && c < 4096; c++) cpus.push_back((int)c);
+        s = (*end == ',') ? end + 1 : end;
+        if (*end != ',') break;
+    }
+    return cpus;
+}
+
+// CPUs local to a CUDA device that this process may run on; empty when unknown or when they are all the
+// CPUs anyway (single-node hosts: nothing to bind)
+std::vector<int> device_local_cpus(int device) {
+    std::vector<int> out;
+    if (!numa_enabled()) return out;
+    char bdf[32] = "";
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, device) != cudaSuccess) {
+        cudaGetLastError();
+        return out;
+    }
+    for (char* c = bdf; *c; c++) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bdf);
+    FILE* f = fopen(path, "r");
+    if (!f) return out;
+    char buf[4096] = "";
+    const bool ok = fgets(buf, sizeof buf, f) != nullptr;
+    fclose(f);
+    if (!ok) return out;
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return out;
+    for (int c : parse_cpulist(buf))
+        if (c < CPU_SETSIZE && CPU_ISSET(c, &allowed)) out.push_back(c);
+    if ((int)out.size() == CPU_COUNT(&allowed)) out.clear();
+    return out;
+}
+
+void bind_this_thread(const std::vector<int>& cpus) {
+    if (cpus.empty()) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    for (int c : cpus)
+        if (c < CPU_SETSIZE) CPU_SET(c, &set);
+    pthread_setaffinity_np(pthread_self(), sizeof set, &set);   // best effort
+}
+
+// RAII: restores the calling thread's affinity mask (the one-device path runs on the caller's thread)
+struct AffinityScope {
+    cpu_set_t saved;
+    bool active = false;
+    explicit AffinityScope(const std::vector<int>& cpus) {
+        if (cpus.empty() || pthread_getaffinity_np(pthread_self(), sizeof saved, &saved) != 0) return;
+        active = true;
+        bind_this_thread(cpus);
+    }
+    ~AffinityScope() {
+        if (active) pthread_setaffinity_np(pthread_self(), sizeof saved, &saved);
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Pageable destination (what R allocates): D2H goes through a small ring of pinned staging slots
@@ -1267,7 +1379,10 @@ public:
 
     ~PageableSink() { finish(); }
 
-    int start() {
+    // n_threads: memcpy fan-out of one slot (the host's cores are shared by the sinks of all devices of the
+    // job); cpus: where those threads (and the drain thread) run — the device's local CPUs, or empty
+    int start(unsigned n_threads, std::vector<int> cpus) {
+        cpus_ = std::move(cpus);
         for (int i = 0; i < kSlots; i++) {
             {   // pinned slots are recycled process-wide (cudaHostAlloc is slow), one set per sink
                 std::lock_guard<std::mutex> lk(pinned_mu());
@@ -1284,8 +1399,11 @@ public:
             if (cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
                 return IPR_ECUDA;
         }
-        n_threads_ = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-        drain_ = std::thread([this] { drain_loop(); });
+        n_threads_ = std::max(1u, n_threads);
+        drain_ = std::thread([this] {
+            bind_this_thread(cpus_);   // the fan-out threads inherit the mask
+            drain_loop();
+        });
         started_ = true;
         return IPR_OK;
     }
@@ -1428,6 +1546,7 @@ private:
     long long issued_ = 0, drained_ = 0;
     bool done_ = false, failed_ = false, started_ = false;
     unsigned n_threads_ = 1;
+    std::vector<int> cpus_;
 };
 
 // IPR_TRACE=1: phase timestamps of the host-buffer path on stderr
@@ -1448,6 +1567,9 @@ int run_device_block(const HostJob& job, int device, long long c0, long long c1,
     Trace tr;
     const int nd = job.n_dates;
     const long long nc = c1 - c0;
+    // this thread and the host-side copy threads of this device stay on the device's local CPUs
+    const std::vector<int> local_cpus = device_local_cpus(device);
+    AffinityScope affinity(local_cpus);
     ipr_plan* plan = nullptr;
     int rc = ipr_plan_create(&plan, device, job.cell_x + c0, job.cell_y + c0, nc, job.st_x, job.st_y, job.n_st, nd, err,
                              errlen);
@@ -1484,42 +1606,46 @@ int run_device_block(const HostJob& job, int device, long long c0, long long c1,
     if (rc) return rc;
     tr.mark("obs uploaded and prepared");
     const int n_stacks = job.cressman ? job.n_radii : 1;
-    // Work items: (stack, date chunk), stack outermost so that the A-operand cache is generated once
-    // per radius.  A chunk is one 128-date granule (1 GB per 10^6 cells): D2H starts after the first
-    // granule and only the last granule's copy is left when the kernels finish.
-    const int chunk = kGran;
-    struct Item { int stack, t0, t1; };
-    std::vector<Item> items;
-    for (int s = 0; s < n_stacks; s++)
-        for (int t = 0; t < nd; t += chunk) {
-            const int te = std::min(nd, t + chunk);
-            // the very first granule goes out as 32 + 96 dates: the copy engine starts after a quarter of
-            // a granule's kernels instead of a whole one (nothing else can overlap with that wait)
-            if (s == 0 && t == 0 && te > 32) {
-                items.push_back({s, 0, 32});
-                items.push_back({s, 32, te});
-            } else {
-                items.push_back({s, t, te});
-            }
-        }
-    const size_t slot_doubles = (size_t)nc * std::min(chunk, (int)round_up(nd, 16));
+    const std::vector<WorkItem> items = make_items(n_stacks, nd);
+    const size_t slot_doubles = (size_t)nc * std::min(kGran, (int)round_up(nd, 16));
     IPR_CUDA(acquire_stream(&g.copy));
     PageableSink sink;
-    if (!job.out_pinned && (rc = sink.start())) {
-        set_err(err, errlen, "could not set up the pinned staging ring for a pageable output buffer");
-        return rc;
+    if (!job.out_pinned) {
+        // the host's cores are shared by the sinks of all devices of the job
+        const unsigned cores = local_cpus.empty() ? std::max(1u, std::thread::hardware_concurrency())
+                                                  : (unsigned)local_cpus.size();
+        const unsigned share = local_cpus.empty() ? cores / (unsigned)std::max(1, job.n_job_devices) : cores;
+        unsigned fan = std::max(2u, std::min(16u, share));
+        if (const char* e = getenv("IPR_DRAIN_THREADS")) fan = (unsigned)std::max(1, atoi(e));
+        if ((rc = sink.start(fan, local_cpus))) {
+            set_err(err, errlen, "could not set up the pinned staging ring for a pageable output buffer");
+            return rc;
+        }
     }
     const int n_ring = std::min<int>(kRing, (int)items.size());
     for (int i = 0; i < n_ring; i++) {
         IPR_CUDA(dev_malloc(&g.ring[i], sizeof(double) * slot_doubles));
-        IPR_CUDA(cudaEventCreateWithFlags(&g.done[i], cudaEventDisableTiming));
+        // the host paces itself on these (cancellation and progress are decided per work item)
+        IPR_CUDA(cudaEventCreateWithFlags(&g.done[i], cudaEventDisableTiming | cudaEventBlockingSync));
         IPR_CUDA(cudaEventCreateWithFlags(&g.computed[i], cudaEventDisableTiming));
     }
     tr.mark("ring allocated");
+    bool cancelled = false;
+    long long reported = 0;
     for (size_t ii = 0; ii < items.size(); ii++) {
-        const Item& it = items[ii];
+        const WorkItem& it = items[ii];
         const int slot = (int)(ii % n_ring);
-        if ((int)ii >= n_ring) IPR_CUDA(cudaStreamWaitEvent(plan->stream, g.done[slot], 0));
+        if ((int)ii >= n_ring) {
+            // the slot's previous chunk has reached the host: the GPU still holds the chunks in between, so
+            // waiting here on the host costs no bubble, and it is where a job is cancelled / reports progress
+            IPR_CUDA(cudaEventSynchronize(g.done[slot]));
+            if (job.done) job.done->fetch_add(1);
+            reported++;
+        }
+        if (job.cancel && job.cancel->load() != 0) {
+            cancelled = true;
+            break;
+        }
         if (job.cressman)
             rc = ipr_plan_cressman(plan, job.radii + it.stack, 1, it.t0, it.t1, g.ring[slot], nc, 0, err, errlen);
         else
@@ -1543,7 +1669,7 @@ int run_device_block(const HostJob& job, int device, long long c0, long long c1,
         }
         IPR_CUDA(cudaEventRecord(g.done[slot], g.copy));
     }
-    tr.mark("all chunks submitted");
+    tr.mark(cancelled ? "cancelled" : "all chunks submitted");
     if ((rc = ipr_plan_sync(plan))) {
         set_err(err, errlen, "stream synchronisation failed");
         return rc;
@@ -1556,7 +1682,19 @@ int run_device_block(const HostJob& job, int device, long long c0, long long c1,
         return rc;
     }
     tr.mark("host staging drained");
+    if (cancelled) {
+        set_err(err, errlen, "cancelled");
+        return IPR_ECANCELLED;
+    }
+    if (job.done) job.done->fetch_add((long long)items.size() - reported);
     return IPR_OK;
+}
+
+// contiguous cell ranges on 64-cell tile boundaries, equal to within one tile (ipr_cell_split_bounds)
+void cell_split(long long n_cells, int G, long long* bounds) {
+    const long long n_tiles = (n_cells + kCellsPerCta - 1) / kCellsPerCta;
+    for (int g = 0; g <= G; g++) bounds[g] = std::min<long long>(n_cells, n_tiles * g / G * kCellsPerCta);
+    bounds[G] = n_cells;
 }
 
 int run_host_job(const HostJob& job, const int* devices, int n_devices, char* err, size_t errlen) {
@@ -1581,22 +1719,28 @@ int run_host_job(const HostJob& job, const int* devices, int n_devices, char* er
         if (e != cudaSuccess) cudaGetLastError();
         jobx.out_pinned = (e == cudaSuccess && attr.type == cudaMemoryTypeHost);
     }
+    if (!jobx.out_pinned && !(getenv("IPR_THP") && atoi(getenv("IPR_THP")) == 0)) {
+        // a fresh pageable result (what R's allocVector returns) is first touched by the staging fan-out: ask
+        // for transparent huge pages so that 29 GB cost ~14 k page faults instead of 7 M (no-op where THP is off)
+        const size_t bytes = sizeof(double) * (size_t)job.n_cells * job.n_dates * (job.cressman ? job.n_radii : 1);
+        const uintptr_t lo = (reinterpret_cast<uintptr_t>(job.out) + 4095) & ~uintptr_t(4095);
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(job.out) + bytes) & ~uintptr_t(4095);
+        if (hi > lo) madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);
+    }
     // Every output element depends only on its own cell and date, so the devices split the
     // CELLS into contiguous ranges on 64-cell tile boundaries: nothing is computed twice (a date split
     // would make every device regenerate all cell x station weights), the shares are equal to within
     // one tile, and each device writes its own column range of every layer.  No inter-GPU exchange.
     std::vector<long long> bounds(G + 1, 0);
-    {
-        const long long n_tiles = (job.n_cells + kCellsPerCta - 1) / kCellsPerCta;
-        for (int g = 0; g <= G; g++) bounds[g] = std::min<long long>(job.n_cells, n_tiles * g / G * kCellsPerCta);
-        bounds[G] = job.n_cells;
-    }
+    cell_split(job.n_cells, G, bounds.data());
+    jobx.n_job_devices = G;
     std::vector<int> rcs(G, IPR_OK);
     std::vector<std::string> errs(G, std::string(256, '\0'));
     auto run_block = [&](int g) {
         char* e = &errs[g][0];
         const size_t n = errs[g].size();
         rcs[g] = no_throw(e, n, [&] { return run_device_block(jobx, devs[g], bounds[g], bounds[g + 1], e, n); });
+        if (rcs[g] != IPR_OK && jobx.cancel) jobx.cancel->store(1);   // no point in finishing the other shares
     };
     if (G == 1) {
         run_block(0);
@@ -1606,17 +1750,135 @@ int run_host_job(const HostJob& job, const int* devices, int n_devices, char* er
         for (auto& t : th) t.join();
     }
     tj.mark("(job) all device blocks done");
+    // a real failure on any device wins over the IPR_ECANCELLED the others report after the job's flag was raised
+    int first = -1;
     for (int g = 0; g < G; g++)
-        if (rcs[g] != IPR_OK) {
-            set_err(err, errlen, "device %d: %s", devs[g], errs[g].c_str());
-            return rcs[g];
-        }
+        if (rcs[g] != IPR_OK && (first < 0 || (rcs[first] == IPR_ECANCELLED && rcs[g] != IPR_ECANCELLED))) first = g;
+    if (first >= 0) {
+        set_err(err, errlen, "device %d: %s", devs[first], errs[first].c_str());
+        return rcs[first];
+    }
     return IPR_OK;
 }
 
 }  // namespace
 
+// asynchronous job: the one-shot call on a worker thread, polled by the host language's main thread
+struct ipr_job {
+    HostJob job;
+    std::vector<int> devs;
+    std::vector<double> radii;        // copied: the caller's radii vector need not outlive the start call
+    std::atomic<int> cancel{0};
+    std::atomic<long long> done{0};
+    long long total = 0;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool finished = false;
+    int rc = IPR_OK;
+    char err[512] = "";
+};
+
+namespace {
+
+int job_start(ipr_job** out, HostJob job, const int* devices, int n_devices, char* err, size_t errlen) {
+    if (!out) {
+        set_err(err, errlen, "NULL argument");
+        return IPR_EINVAL;
+    }
+    *out = nullptr;
+    return no_throw(err, errlen, [&] {
+        std::unique_ptr<ipr_job> j(new ipr_job());
+        j->job = job;
+        if (job.cressman) {
+            j->radii.assign(job.radii, job.radii + job.n_radii);
+            j->job.radii = j->radii.data();
+        }
+        if (devices && n_devices > 0) j->devs.assign(devices, devices + n_devices);
+        else j->devs.push_back(0);
+        j->job.cancel = &j->cancel;
+        j->job.done = &j->done;
+        const int n_stacks = job.cressman ? job.n_radii : 1;
+        j->total = (long long)make_items(n_stacks, std::max(job.n_dates, 1)).size() * (long long)j->devs.size();
+        ipr_job* p = j.get();
+        p->th = std::thread([p] {
+            const int rc = no_throw(p->err, sizeof p->err, [&] {
+                return run_host_job(p->job, p->devs.data(), (int)p->devs.size(), p->err, sizeof p->err);
+            });
+            std::lock_guard<std::mutex> lk(p->mu);
+            p->rc = rc;
+            p->finished = true;
+            p->cv.notify_all();
+        });
+        *out = j.release();
+        return IPR_OK;
+    });
+}
+
+}  // namespace
+
 extern "C" {
+
+int ipr_job_start_idw(ipr_job** job, const double* cell_x, const double* cell_y, int64_t n_cells, const double* st_x,
+                      const double* st_y, int32_t n_st, const double* obs, int32_t n_dates, double p,
+                      int32_t round_mode, int32_t n_round, const uint8_t* cell_keep, const int* devices, int n_devices,
+                      double* out, char* err, size_t errlen) {
+    HostJob hj{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, false, p, nullptr, 0, out};
+    hj.round_mode = round_mode;
+    hj.n_round = n_round;
+    hj.cell_keep = cell_keep;
+    return job_start(job, hj, devices, n_devices, err, errlen);
+}
+
+int ipr_job_start_cressman(ipr_job** job, const double* cell_x, const double* cell_y, int64_t n_cells,
+                           const double* st_x, const double* st_y, int32_t n_st, const double* obs, int32_t n_dates,
+                           const double* radii_m, int32_t n_radii, int32_t round_mode, int32_t n_round,
+                           const uint8_t* cell_keep, const int* devices, int n_devices, double* out, char* err,
+                           size_t errlen) {
+    if (!radii_m || n_radii <= 0) {
+        set_err(err, errlen, "radii_m must hold at least one radius");
+        return IPR_EINVAL;
+    }
+    HostJob hj{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, true, 2.0, radii_m, n_radii, out};
+    hj.round_mode = round_mode;
+    hj.n_round = n_round;
+    hj.cell_keep = cell_keep;
+    return job_start(job, hj, devices, n_devices, err, errlen);
+}
+
+int ipr_job_wait(ipr_job* job, int timeout_ms, int64_t* done, int64_t* total) {
+    if (!job) return IPR_EINVAL;
+    bool fin;
+    {
+        std::unique_lock<std::mutex> lk(job->mu);
+        if (timeout_ms < 0) job->cv.wait(lk, [&] { return job->finished; });
+        else job->cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return job->finished; });
+        fin = job->finished;
+    }
+    if (done) *done = std::min<long long>(job->done.load(), job->total);
+    if (total) *total = job->total;
+    return fin ? 1 : 0;
+}
+
+void ipr_job_cancel(ipr_job* job) {
+    if (job) job->cancel.store(1);
+}
+
+int ipr_job_finish(ipr_job* job, char* err, size_t errlen) {
+    if (!job) return IPR_EINVAL;
+    if (job->th.joinable()) job->th.join();
+    const int rc = job->rc;
+    if (rc != IPR_OK) set_err(err, errlen, "%s", job->err);
+    delete job;
+    return rc;
+}
+
+void ipr_cell_split_bounds(int64_t n_cells, int n_devices, int64_t* bounds) {
+    if (!bounds || n_devices < 1) return;
+    std::vector<long long> b((size_t)n_devices + 1, 0);
+    cell_split(std::max<long long>(n_cells, 0), n_devices, b.data());
+    for (int g = 0; g <= n_devices; g++) bounds[g] = b[g];
+}
 
 int ipr_idw_f64(const double* cell_x, const double* cell_y, int64_t n_cells, const double* st_x, const double* st_y,
                 int32_t n_st, const double* obs, int32_t n_dates, double p, const int* devices, int n_devices,

@@ -579,11 +579,11 @@ __global__ void zero_pairs_kernel(const double2* __restrict__ cell_xy, long long
 //   fix_cell[i], fix_off[i]..fix_off[i+1] -> fix_st[] (ascending station index)
 // ---------------------------------------------------------------------------------------------
 __global__ void idw_zero_fix_kernel(const int* __restrict__ fix_cell, const int* __restrict__ fix_off,
-                                    const int* __restrict__ fix_st, int n_fix, const double* __restrict__ obs,
+                                    const int* __restrict__ fix_st, int fix0, int n_fix, const double* __restrict__ obs,
                                     long long ld_obs, const uint8_t* __restrict__ date_flag, int t_lo, int t_hi,
                                     double* __restrict__ out, long long ld_out) {
     const int t = t_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
+    const int i = fix0 + blockIdx.y;   // gridDim.y is capped at 65535: the host launches the list in slices
     if (t >= t_hi || i >= n_fix) return;
     if (date_flag[t] != 0) return;
     double pred = 0.0;

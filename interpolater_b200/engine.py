@@ -116,6 +116,96 @@ def cressman_grid(cell_x, cell_y, st_x, st_y, obs, radii_m, devices=None, out=No
     return flat.reshape(rad.shape[0], n_dates, n_cells).transpose(0, 2, 1)
 
 
+def cell_split_bounds(n_cells, n_devices):
+    """The cell ranges the one-shot calls give to `n_devices` GPUs (ipr_cell_split_bounds): device g owns
+    cells [b[g], b[g+1])."""
+    b = (C.c_int64 * (n_devices + 1))()
+    _native.load().ipr_cell_split_bounds(int(n_cells), int(n_devices), b)
+    return [int(v) for v in b]
+
+
+class Job:
+    """Asynchronous one-shot call (ipr_job_*): the job runs on the library's worker threads while the caller
+    polls — the shape the R shim uses to keep R's main thread free for the progress bar of R/IDW.R:350-352
+    and for user interrupts.  ``Job.idw(...)`` / ``Job.cressman(...)`` start, ``wait(ms)`` polls and
+    returns (finished, done, total), ``cancel()`` asks to stop, ``finish()`` joins and returns the array
+    (raises NativeError, code IPR_ECANCELLED after a cancel)."""
+
+    def __init__(self):
+        self._lib = _native.load()
+        self._h = C.c_void_p()
+        self._keep = None
+        self._result = None
+
+    @classmethod
+    def idw(cls, cell_x, cell_y, st_x, st_y, obs, p=2.0, devices=None, n_round=None, round_mode=ROUND_R,
+            cell_keep=None):
+        self = cls()
+        cx, cy = _f64(cell_x, "cell_x"), _f64(cell_y, "cell_y")
+        sx, sy = _f64(st_x, "st_x"), _f64(st_y, "st_y")
+        ob = _obs_colmajor(obs, sx.shape[0])
+        out = np.empty((cx.shape[0], ob.shape[0]), dtype=np.float64, order="F")
+        dev, ndev = _devices(devices)
+        rmode, nr, keep = _post_args(n_round, round_mode, cell_keep, cx.shape[0])
+        err = _native.errbuf()
+        self._keep = (cx, cy, sx, sy, ob, keep, dev, out)   # must outlive the job
+        rc = self._lib.ipr_job_start_idw(C.byref(self._h), cx.ctypes.data, cy.ctypes.data, cx.shape[0], sx.ctypes.data,
+                                         sy.ctypes.data, sx.shape[0], ob.ctypes.data, ob.shape[0], float(p), rmode, nr,
+                                         keep.ctypes.data if keep is not None else None, dev, ndev, out.ctypes.data,
+                                         err, _native.ERRLEN)
+        _native.check(rc, err)
+        self._result = out
+        return self
+
+    @classmethod
+    def cressman(cls, cell_x, cell_y, st_x, st_y, obs, radii_m, devices=None, n_round=None, round_mode=ROUND_TERRA,
+                 cell_keep=None):
+        self = cls()
+        cx, cy = _f64(cell_x, "cell_x"), _f64(cell_y, "cell_y")
+        sx, sy = _f64(st_x, "st_x"), _f64(st_y, "st_y")
+        ob = _obs_colmajor(obs, sx.shape[0])
+        rad = _f64(radii_m, "radii_m")
+        flat = np.empty(rad.shape[0] * cx.shape[0] * ob.shape[0], dtype=np.float64)
+        dev, ndev = _devices(devices)
+        rmode, nr, keep = _post_args(n_round, round_mode, cell_keep, cx.shape[0])
+        err = _native.errbuf()
+        self._keep = (cx, cy, sx, sy, ob, keep, dev, flat)
+        rc = self._lib.ipr_job_start_cressman(C.byref(self._h), cx.ctypes.data, cy.ctypes.data, cx.shape[0],
+                                              sx.ctypes.data, sy.ctypes.data, sx.shape[0], ob.ctypes.data, ob.shape[0],
+                                              rad.ctypes.data, rad.shape[0], rmode, nr,
+                                              keep.ctypes.data if keep is not None else None, dev, ndev,
+                                              flat.ctypes.data, err, _native.ERRLEN)
+        _native.check(rc, err)
+        self._result = flat.reshape(rad.shape[0], ob.shape[0], cx.shape[0]).transpose(0, 2, 1)
+        return self
+
+    def wait(self, timeout_ms=100):
+        done, total = C.c_int64(), C.c_int64()
+        fin = self._lib.ipr_job_wait(self._h, int(timeout_ms), C.byref(done), C.byref(total))
+        if fin < 0:
+            raise _native.NativeError(fin, "job handle is not valid")
+        return bool(fin), int(done.value), int(total.value)
+
+    def cancel(self):
+        self._lib.ipr_job_cancel(self._h)
+
+    def finish(self):
+        err = _native.errbuf()
+        h, self._h = self._h, C.c_void_p()
+        rc = self._lib.ipr_job_finish(h, err, _native.ERRLEN)
+        res, self._result, self._keep = self._result, None, None
+        _native.check(rc, err)
+        return res
+
+    def __del__(self):
+        try:
+            if self._h:
+                self.cancel()
+                self._lib.ipr_job_finish(self._h, None, 0)
+        except Exception:
+            pass
+
+
 class Plan:
     """Device-resident plan (include/interpolater_b200.h, ipr_plan_*): inputs live in HBM, outputs
     are written to caller-supplied device pointers (e.g. ``torch.Tensor.data_ptr()``)."""

@@ -649,3 +649,156 @@ def test_full_size_properties_masked_and_cressman():
     for ri in range(radii.size):
         assert_parity(gotc[ri].T, wantc[ri], label=f"full-size Cressman sample R={radii[ri]:.0f}")
     plan.close()
+
+
+# ---------------------------------------------------------------- full records, drop-in signature at full size
+def test_full_size_full_record_all_dates_sampled_cells():
+    """cfg 3 at its full size AND full length: 1,000,000 cells x 2,000 stations x 3,650 days through the
+    29-tile launch path with the ragged 66-date last granule; 1,000 seeded cells x every date against the
+    oracle (matrix form, held to the literal per-date loop by tests/test_oracle.py)."""
+    import torch
+
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(1000, 1000, 2000, 3650, all_na_dates=(3649,), all_zero_dates=(3600,))
+    plan = engine.Plan(0, cx, cy, sx, sy, 3650)
+    out = torch.empty((3650, cx.size), dtype=torch.float64, device="cuda")
+    plan.set_obs(obs)
+    plan.idw(out.data_ptr())
+    plan.sync()
+    idx = np.sort(np.random.default_rng(5).choice(cx.size, 1000, replace=False))
+    got = out[:, torch.from_numpy(idx).cuda()].cpu().numpy().T
+    assert_parity(got, ref.idw_reference_matrix(cx[idx], cy[idx], sx, sy, obs, 2.0), label="cfg 3, all 3650 dates")
+    assert bool(out[3649].isnan().all()) and bool((out[3600] == 0).all())
+    assert bool(torch.isfinite(out[3584:3649]).all())          # the ragged last granule, every cell
+    plan.close()
+
+
+def test_full_size_cfg5_through_the_drop_in_signature():
+    """BASELINE.json configs[4] at full size through the reference's own signature: 1,000,000-cell grid,
+    2,000 stations with 20 % per-date NA, 400 of them held out as stat_validation, 3,650 days.  The
+    validation table must equal what the oracle derives at the 400 test-station cells (IDW at those cells
+    from the 1,600 training stations -> R's round -> gof), and a seeded sample of the returned stack must
+    match the oracle on every date."""
+    import pandas as pd
+
+    ncol = nrow = 1000
+    n_st, n_dates = 2000, 3650
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(ncol, nrow, n_st, n_dates, na_frac=0.2, seed=505)
+    names = [f"S{i:04d}" for i in range(n_st)]
+    dates = pd.date_range("2001-01-01", periods=n_dates, freq="D")
+    BD_Obs = pd.concat([pd.DataFrame({"Date": dates}), pd.DataFrame(obs, columns=names)], axis=1)
+    BD_Coord = pd.DataFrame({"Cod": names, "X": sx, "Y": sy, "Z": 0.0})
+    held_idx = np.sort(np.random.default_rng(20260105).choice(n_st, 400, replace=False))
+    held = [names[i] for i in held_idx]
+    shp = ipr.SpatVector.from_bbox(200000.0, 200000.0 + ncol * 1000.0, 9000000.0, 9000000.0 + nrow * 1000.0)
+    out = ipr.IDW(BD_Obs, BD_Coord, shp, grid_resolution=1, p=2, Mask=False, n_round=1, stat_validation=held)
+    ens, tab = out["Ensamble"], out["Validation"]
+    assert ens.nlyr() == n_dates and ens.values.shape == (ncol * nrow, n_dates)
+    ti = np.array([i for i in range(n_st) if names[i] not in set(held)])       # names are already Cod-sorted
+    # (1) a seeded sample of the stack, every date
+    idx = np.sort(np.random.default_rng(6).choice(cx.size, 300, replace=False))
+    want = ref.idw_reference_matrix(cx[idx], cy[idx], sx[ti], sy[ti], obs[:, ti], 2.0)
+    got = ens.values[idx, :]
+    want_r = np.round(want, 1)
+    close = np.isclose(got, want_r, rtol=0, atol=1e-12) | (np.isnan(got) & np.isnan(want_r))
+    # 1-digit rounding may flip on values within 1e-12 of a tie (x.x5): a handful at most, never more than 0.1
+    assert (~close).sum() <= 5 and np.nanmax(np.abs(got - want)) <= 0.05 + 1e-9
+    # (2) the validation table against the oracle evaluated at the test-station cells
+    grid = ref.grid_from_extent(200000.0, 200000.0 + ncol * 1000.0, 9000000.0, 9000000.0 + nrow * 1000.0, 1000.0)
+    assert tab["ID"].tolist() == held
+    wv = ref.validate_reference(grid, ens.values, sx[held_idx], sy[held_idx], obs[:, held_idx])
+    for j, row in enumerate(wv):
+        for k in ref.GOF_COLUMNS:
+            a, b = float(tab[k].iloc[j]), row["gof"][k]
+            assert (np.isnan(a) and np.isnan(b)) or a == b, (j, k, a, b)
+    # ... and independently of the engine's stack: oracle IDW at those cells
+    cells = np.array(ref.extract_cells(grid, sx[held_idx], sy[held_idx]))
+    sim = ref.idw_reference_matrix(cx[cells], cy[cells], sx[ti], sy[ti], obs[:, ti], 2.0)
+    eng = ens.values[cells, :]
+    assert np.nanmax(np.abs(eng - sim)) <= 0.05 + 1e-9 and np.array_equal(np.isnan(eng), np.isnan(sim))
+
+
+# ---------------------------------------------------------------- more than one physical GPU
+def test_all_visible_gpus_equal_one_device():
+    """The product entry point over every visible GPU (one process, a host thread + plan per device, each
+    device writing its column range of the caller's matrix) against the one-device run: same cells, same
+    arithmetic -> bit-equal for Cressman (one code path), equal to summation order for IDW."""
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one visible GPU: the scheduler itself is covered by test_multi_device_scheduler_on_one_gpu")
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(300, 257, 333, 700, na_frac=0.08, plant_zero_dist=4,
+                                                   all_na_dates=(11,), all_zero_dates=(12,), seed=88)
+    devs = list(range(n))
+    one = engine.idw_grid(cx, cy, sx, sy, obs, devices=[0])
+    many = engine.idw_grid(cx, cy, sx, sy, obs, devices=devs)
+    assert np.array_equal(np.isnan(one), np.isnan(many))
+    assert_parity(many, one, tol=1e-12, label=f"IDW on devices {devs}")
+    b = engine.cell_split_bounds(cx.size, n)
+    sample = np.concatenate([np.arange(b[g], min(b[g] + 50, b[g + 1])) for g in range(n)])
+    assert_parity(many[sample], ref.idw_reference(cx[sample], cy[sample], sx, sy, obs, 2.0), label="multi-GPU vs oracle")
+    radii = np.array([6e3, 25e3, 90e3])
+    c1 = np.ascontiguousarray(engine.cressman_grid(cx, cy, sx, sy, obs, radii, devices=[0]))
+    cn = np.ascontiguousarray(engine.cressman_grid(cx, cy, sx, sy, obs, radii, devices=devs))
+    assert np.array_equal(c1, cn, equal_nan=True)
+    # pinned caller buffer: cudaMemcpy2DAsync straight into the column ranges
+    lib = _native.load()
+    import ctypes as Ct
+    nbytes = cx.size * obs.shape[0] * 8
+    hp = lib.ipr_host_alloc(nbytes)
+    try:
+        buf = np.ctypeslib.as_array((Ct.c_double * (nbytes // 8)).from_address(hp)).reshape(obs.shape[0], cx.size).T
+        engine.idw_grid(cx, cy, sx, sy, obs, devices=devs, out=buf)
+        assert np.array_equal(buf, many, equal_nan=True)
+    finally:
+        lib.ipr_host_free(hp)
+
+
+# ---------------------------------------------------------------- asynchronous jobs (progress, cancel)
+def test_job_api_progress_and_result():
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(120, 90, 150, 1100, na_frac=0.1, plant_zero_dist=2, seed=21)
+    want = engine.idw_grid(cx, cy, sx, sy, obs)
+    job = engine.Job.idw(cx, cy, sx, sy, obs)
+    seen = []
+    while True:
+        fin, done, total = job.wait(5)
+        seen.append(done)
+        if fin:
+            break
+    assert total == 10 and seen[-1] == total and seen == sorted(seen)   # 9 granules, the first one split in two
+    assert np.array_equal(job.finish(), want, equal_nan=True)
+    radii = np.array([5e3, 3e4])
+    jobc = engine.Job.cressman(cx, cy, sx, sy, obs, radii, devices=[0, 0])
+    fin, done, total = jobc.wait(-1)
+    assert fin and done == total == 2 * (2 * 9 + 1)
+    assert np.array_equal(np.ascontiguousarray(jobc.finish()),
+                          np.ascontiguousarray(engine.cressman_grid(cx, cy, sx, sy, obs, radii)), equal_nan=True)
+
+
+def test_job_cancel_returns_cancelled_and_leaves_the_library_usable():
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(400, 400, 500, 3000, seed=22)
+    job = engine.Job.idw(cx, cy, sx, sy, obs)
+    job.wait(20)
+    job.cancel()
+    with pytest.raises(_native.NativeError) as ei:
+        job.finish()
+    assert ei.value.code == _native.IPR_ECANCELLED
+    small = synthetic.synthetic_case(20, 20, 30, 40, seed=23)
+    assert_parity(engine.idw_grid(*small), ref.idw_reference(*small, 2.0), label="after a cancelled job")
+
+
+def test_more_than_65535_colocated_cells():
+    """A grid whose stations are snapped to cell centres: more zero-distance cells than one grid.y
+    dimension holds.  Every such cell takes its station's observation (running mean of one, R/IDW.R:310-326)."""
+    ncol = nrow = 300
+    n_st = 70000
+    cx, cy = synthetic.regular_grid(ncol, nrow)
+    rng = np.random.default_rng(9)
+    cells = rng.choice(ncol * nrow, n_st, replace=False)
+    obs = np.round(rng.gamma(0.8, 8.0, (3, n_st)), 1) + 0.1
+    obs[1, ::7] = np.nan
+    got = engine.idw_grid(cx, cy, cx[cells], cy[cells], obs)
+    for t in range(3):
+        ok = ~np.isnan(obs[t])
+        assert np.array_equal(got[cells[ok], t], obs[t, ok])
+    assert not np.isnan(got).any()
