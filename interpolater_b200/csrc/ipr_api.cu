@@ -53,6 +53,19 @@ void set_err(char* err, size_t errlen, const char* fmt, ...) {
 
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
+// IPR_TRACE=1: phase timestamps of the host-buffer path on stderr
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(getenv("IPR_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[ipr trace] %8.2f ms  %s\n", ms, what);
+    }
+};
+
+
 // No C++ exception may cross the C ABI (the caller is R's .Call or ctypes): host allocations of the
 // staging vectors are the realistic source.
 template <class F>
@@ -189,7 +202,7 @@ void dev_free(void* ptr) {
 inline double canon_zero(double v) { return v == 0.0 ? 0.0 : v; }  // -0 -> +0
 
 // Z-order (Morton) sort of points on a 65536^2 lattice spanning their bounding box
-std::vector<int> morton_order(const double* x, const double* y, int n) {
+std::vector<int> morton_order(const double* x, const double* y, int n, int xdiv = 1) {
     double x0 = x[0], x1 = x[0], y0 = y[0], y1 = y[0];
     for (int i = 1; i < n; i++) {
         x0 = std::min(x0, x[i]); x1 = std::max(x1, x[i]);
@@ -206,7 +219,7 @@ std::vector<int> morton_order(const double* x, const double* y, int n) {
     };
     std::vector<std::pair<uint64_t, int>> key(n);
     for (int i = 0; i < n; i++) {
-        const uint32_t ix = (uint32_t)std::min(65535.0, (x[i] - x0) / span * 65535.0);
+        const uint32_t ix = (uint32_t)std::min(65535.0, (x[i] - x0) / span * 65535.0) / (uint32_t)xdiv;
         const uint32_t iy = (uint32_t)std::min(65535.0, (y[i] - y0) / span * 65535.0);
         key[i] = {spread(ix) | (spread(iy) << 1), i};
     }
@@ -277,12 +290,19 @@ struct ipr_plan {
     int* d_run_perm = nullptr;    // Morton order of the 8-cell runs: 8 consecutive entries = one compact cell tile
     std::vector<double2> h_run_xy;   // first cell of every run; d_run_perm is built from it on the first Cressman call
     bool run_perm_ready = false;
+    std::map<int, int*> run_perm_alt;   // the same with x compressed by 4 / 16 / 64: flatter tiles (ensure_run_perm_alt)
     unsigned long long* d_active_total = nullptr;
     unsigned long long stage_tiles_total = 0;  // (cell tile, stage) blocks the dense product would visit
     int w_chunk_tiles = 0;   // capacity of d_wfrag in cell tiles
     int w_mode = -1;         // what the cache currently holds: weight mode, parameter, first tile
     double w_param = 0.0;
     int w_tile0 = -1;
+    // Cressman: per-CTA scratch of the persistent kernel (station list + A panel of the CTA's current cell tile)
+    double* d_cr_panel = nullptr;
+    int* d_cr_list = nullptr;
+    int* d_cr_counter = nullptr;
+    double st_bbox_area = 0.0;   // of the stations' bounding box: station density for the Cressman tile-shape choice
+    int cr_grid = 0;
     // optional per-phase event timing (ipr_plan_profile)
     bool prof_on = false;
     int phase_radius = -1;   // Cressman: radius index of the contraction being launched
@@ -365,6 +385,34 @@ int ensure_run_perm(ipr_plan* p, char* err, size_t errlen) {
                              p->stream));
     IPR_CUDA(cudaStreamSynchronize(p->stream));   // the staging vector goes out of scope
     p->run_perm_ready = true;
+    return IPR_OK;
+}
+
+// Flatter cell tiles for the store-bound radii: the Morton sort with x divided by `xdiv` groups 2 runs x 4 rows
+// (xdiv 4: 128-byte pieces of a layer row per tile), 4 runs x 2 rows (16: 256 B) or 8 runs x 1 row (64: 512 B)
+// instead of 1 run x 8 rows (64 B).  Longer pieces are what the HBM write stream wants; squarer tiles see fewer
+// stations.  Built on first use, kept for the plan's lifetime.
+int ensure_run_perm_alt(ipr_plan* p, int xdiv, const int** d_perm, char* err, size_t errlen) {
+    if (xdiv <= 1) {
+        *d_perm = p->d_run_perm;
+        return ensure_run_perm(p, err, errlen);
+    }
+    auto it = p->run_perm_alt.find(xdiv);
+    if (it == p->run_perm_alt.end()) {
+        const int n_runs = (int)p->h_run_xy.size();
+        std::vector<double> rx(n_runs), ry(n_runs);
+        for (int i = 0; i < n_runs; i++) {
+            rx[i] = p->h_run_xy[i].x;
+            ry[i] = p->h_run_xy[i].y;
+        }
+        const std::vector<int> perm = morton_order(rx.data(), ry.data(), n_runs, xdiv);
+        int* d = nullptr;
+        IPR_CUDA(dev_malloc(&d, sizeof(int) * perm.size()));
+        it = p->run_perm_alt.emplace(xdiv, d).first;
+        IPR_CUDA(cudaMemcpyAsync(d, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice, p->stream));
+        IPR_CUDA(cudaStreamSynchronize(p->stream));   // the staging vector goes out of scope
+    }
+    *d_perm = it->second;
     return IPR_OK;
 }
 
@@ -663,6 +711,117 @@ void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, TileSets& ts)
     }
 }
 
+// IPR_CRESSMAN_LEGACY=1: the round-1 path (weights pass per radius + one CTA per (cell tile, date tile)), kept for A/B
+bool cressman_legacy() {
+    static const bool v = getenv("IPR_CRESSMAN_LEGACY") && atoi(getenv("IPR_CRESSMAN_LEGACY")) != 0;
+    return v;
+}
+
+// Cressman, one radius: the fused persistent kernel (station lists + weights + contraction), one launch per
+// group of at most kMaxTilesPerLaunch date tiles.
+template <int NP, int KS>
+int launch_cressman(ipr_plan* p, CressmanArgs& c, const std::vector<int>& tiles, char* err, size_t errlen) {
+    static std::atomic<bool> configured[64];
+    auto kern = cressman_kernel<NP, KS>;
+    if (!configured[p->device & 63]) {
+        IPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CrLayout<KS>::kTotal));
+        configured[p->device & 63] = true;
+    }
+    for (size_t i0 = 0; i0 < tiles.size(); i0 += kMaxTilesPerLaunch) {
+        const int n = (int)std::min<size_t>(kMaxTilesPerLaunch, tiles.size() - i0);
+        c.tiles.n = n;
+        for (int i = 0; i < n; i++) c.tiles.t0[i] = tiles[i0 + i];
+        IPR_CUDA(cudaMemsetAsync(p->d_cr_counter, 0, sizeof(int), p->stream));
+        kern<<<(unsigned)std::min(c.n_cell_tiles, p->cr_grid), kThreads, CrLayout<KS>::kTotal, p->stream>>>(c);
+        IPR_CUDA(cudaGetLastError());
+        p->launches++;
+    }
+    return IPR_OK;
+}
+
+int run_cressman_radius(ipr_plan* p, double radius_m, int t0, int t1, double* d_out, long long ld_out, char* err,
+                        size_t errlen) {
+    // Cell-tile shape by the expected length of a tile's station list (n_st x disc / bounding box).  Short lists:
+    // the kernel is bound by the 29 GB store stream of the stack, which wants long contiguous pieces of a layer
+    // row per tile (measured on cfg 4 at 25 km: 14.1 / 12.2 / 10.1 / 9.0 ms for 64 / 128 / 256 / 512-byte pieces);
+    // long lists: bound by the DMMA pipe, which wants square tiles (fewest stations in reach of any cell).
+    const double est_list = p->st_bbox_area > 0.0
+                                ? std::min((double)p->n_st, p->n_st * 3.141592653589793 * radius_m * radius_m / p->st_bbox_area)
+                                : (double)p->n_st;
+    int xdiv = est_list < 10.0 ? 64 : est_list < 40.0 ? 4 : 1;
+    if (const char* e = getenv("IPR_CR_XDIV")) xdiv = atoi(e);   // 1, 4, 16, 64: override for experiments
+    const int* d_perm = nullptr;
+    int rc = ensure_run_perm_alt(p, xdiv, &d_perm, err, errlen);
+    if (rc) return rc;
+    const int list_cap = (int)round_up(p->n_st, kCrListPad);
+    if (!p->d_cr_panel) {
+        int n_sm = 0;
+        IPR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
+        p->cr_grid = 2 * n_sm;   // two resident CTAs per SM
+        IPR_CUDA(dev_malloc(&p->d_cr_panel, sizeof(double) * (size_t)p->cr_grid * list_cap * kCellsPerCta));
+        IPR_CUDA(dev_malloc(&p->d_cr_list, sizeof(int) * (size_t)p->cr_grid * list_cap));
+        IPR_CUDA(dev_malloc(&p->d_cr_counter, sizeof(int) * 32));
+    }
+    TileSets ts;
+    build_tiles(p, t0, t1, false, ts);
+    std::vector<int> tiles;
+    int np = 2;
+    for (int w : {2, 4, 6, 8})
+        if (!ts.u[w].empty()) {
+            np = w;
+            tiles.insert(tiles.end(), ts.u[w].begin(), ts.u[w].end());
+        }
+    std::sort(tiles.begin(), tiles.end());
+    CressmanArgs c{};
+    c.cell_xy = p->d_cell;
+    c.st_xy = p->d_st;
+    c.group_box = p->d_stage_box;
+    c.run_perm = d_perm;
+    c.z0 = p->d_z0;
+    c.out = d_out;
+    c.ld_out = ld_out;
+    c.n_cells = p->n_cells;
+    c.n_cell_tiles = (int)(p->c_pad / kCellsPerCta);
+    c.n_st = p->n_st;
+    c.s_pad = p->s_pad;
+    c.n_groups = p->n_stages * kSubStages;
+    c.r = radius_m;
+    c.r2 = radius_m * radius_m;
+    c.t_lo = t0;
+    c.t_hi = t1;
+    c.panel = p->d_cr_panel;
+    c.list = p->d_cr_list;
+    c.list_cap = list_cap;
+    c.active_total = p->d_active_total;
+    c.tile_counter = p->d_cr_counter;
+    static unsigned long long* d_prof = nullptr;
+    if (getenv("IPR_CR_PROF")) {
+        if (!d_prof) IPR_CUDA(cudaMalloc(&d_prof, 64));
+        IPR_CUDA(cudaMemsetAsync(d_prof, 0, 64, p->stream));
+        c.prof = d_prof;
+    }
+    const size_t n_launch = (tiles.size() + kMaxTilesPerLaunch - 1) / kMaxTilesPerLaunch;
+    p->stage_tiles_total += (unsigned long long)c.n_cell_tiles * c.n_groups * n_launch;
+    PhaseScope ps(p, IPR_PHASE_RADIUS0 + std::min(std::max(p->phase_radius, 0), 23));
+    // the widest tile of the call decides the instantiation; narrower (ragged) tiles mask their stores
+    // (16-station stages, KS = 4, were measured too: 57.1 against 56.5 ms at 200 km, 20.5 against 19.7 at 100 km)
+    switch (np) {
+        case 8: rc = launch_cressman<8, 2>(p, c, tiles, err, errlen); break;
+        case 6: rc = launch_cressman<6, 2>(p, c, tiles, err, errlen); break;
+        case 4: rc = launch_cressman<4, 2>(p, c, tiles, err, errlen); break;
+        default: rc = launch_cressman<2, 2>(p, c, tiles, err, errlen); break;
+    }
+    if (c.prof && rc == IPR_OK) {
+        unsigned long long h[8];
+        IPR_CUDA(cudaStreamSynchronize(p->stream));
+        IPR_CUDA(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+        const double per = 1.0 / ((double)std::min(c.n_cell_tiles, p->cr_grid) * kConsumerWarps);
+        fprintf(stderr, "[cr prof] R=%.0f km, cycles per warp: prepare %.0f  pre-wait %.0f  wait %.0f  mma %.0f  release %.0f  epilogue %.0f  (duty: empty-wait %.0f  gather issue %.0f)\n",
+                radius_m / 1000.0, h[0] * per, h[1] * per, h[2] * per, h[3] * per, h[4] * per, h[5] * per, h[6] * per, h[7] * per);
+    }
+    return rc;
+}
+
 int run_post(ipr_plan* p, int t0, int t1, double* d_out, long long ld_out, char* err, size_t errlen) {
     if (p->post_round_mode == 0 && !p->d_cell_keep) return IPR_OK;
     dim3 grid((unsigned)((p->n_cells + 255) / 256), (unsigned)std::min(t1 - t0, 64));
@@ -851,20 +1010,34 @@ static int plan_create_impl(ipr_plan** plan, int device, const double* cell_x, c
         set_err(err, errlen, "n_cells > 2e9 is not supported");
         return IPR_EUNSUPPORTED;
     }
-    int ndev = 0;
-    IPR_CUDA(cudaGetDeviceCount(&ndev));
+    // device count and compute capability are queried once per process: cudaGetDeviceProperties was traced at
+    // 2-25 ms per call (IPR_TRACE), the whole variable part of a 540 ms host-buffer call
+    static std::mutex dev_mu;
+    static int ndev = -1;
+    static int cc[64][2];
+    {
+        std::lock_guard<std::mutex> lk(dev_mu);
+        if (ndev < 0) {
+            int n = 0;
+            IPR_CUDA(cudaGetDeviceCount(&n));
+            for (int i = 0; i < n && i < 64; i++) {
+                IPR_CUDA(cudaDeviceGetAttribute(&cc[i][0], cudaDevAttrComputeCapabilityMajor, i));
+                IPR_CUDA(cudaDeviceGetAttribute(&cc[i][1], cudaDevAttrComputeCapabilityMinor, i));
+            }
+            ndev = std::min(n, 64);
+        }
+    }
     if (device < 0 || device >= ndev) {
         set_err(err, errlen, "device %d not available (%d visible)", device, ndev);
         return IPR_ECUDA;
     }
-    cudaDeviceProp prop;
-    IPR_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
+    if (cc[device][0] != 10) {
         set_err(err, errlen, "device %d is sm_%d%d; this engine is built for sm_100a only (no fallback)", device,
-                prop.major, prop.minor);
+                cc[device][0], cc[device][1]);
         return IPR_EUNSUPPORTED;
     }
     IPR_CUDA(cudaSetDevice(device));
+    Trace tr;
     // destroyed on every early return (error codes and exceptions alike)
     std::unique_ptr<ipr_plan, void (*)(ipr_plan*)> holder(new ipr_plan(), ipr_plan_destroy);
     ipr_plan* p = holder.get();
@@ -916,6 +1089,7 @@ static int plan_create_impl(ipr_plan** plan, int device, const double* cell_x, c
     IPR_CUDA(cudaMemsetAsync(p->d_mask, 0, sizeof(double) * p->z_doubles, p->stream));
     IPR_CUDA(cudaMemsetAsync(p->d_flag, 0, (size_t)p->n_gran * kGran, p->stream));
     IPR_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(int) * 4, p->stream));
+    tr.mark("(plan) buffers acquired, memsets queued");
     {
         std::vector<double2> h(p->c_pad);
         for (long long i = 0; i < p->c_pad; i++) {
@@ -926,17 +1100,27 @@ static int plan_create_impl(ipr_plan** plan, int device, const double* cell_x, c
                 return IPR_EINVAL;
             }
         }
+        tr.mark("(plan) cell coordinates staged on the host");
         IPR_CUDA(cudaMemcpyAsync(p->d_cell, h.data(), sizeof(double2) * p->c_pad, cudaMemcpyHostToDevice, p->stream));
         // cell tiles for Cressman are 8 Morton-consecutive runs of 8 consecutive cells (ensure_run_perm);
         // the sort costs ~10 ms per 10^6 cells on the host, so it waits for the first Cressman call
         p->h_run_xy.resize((size_t)(p->c_pad / 8));
         for (size_t i = 0; i < p->h_run_xy.size(); i++) p->h_run_xy[i] = h[i * 8];
         IPR_CUDA(cudaStreamSynchronize(p->stream));
+        tr.mark("(plan) cell coordinates uploaded (stream synchronised)");
         for (int i = 0; i < n_st; i++) {
             if (!std::isfinite(st_x[i]) || !std::isfinite(st_y[i])) {
                 set_err(err, errlen, "station coordinate %d is not finite", i);
                 return IPR_EINVAL;
             }
+        }
+        {
+            double x0 = st_x[0], x1 = st_x[0], y0 = st_y[0], y1 = st_y[0];
+            for (int i = 1; i < n_st; i++) {
+                x0 = std::min(x0, st_x[i]); x1 = std::max(x1, st_x[i]);
+                y0 = std::min(y0, st_y[i]); y1 = std::max(y1, st_y[i]);
+            }
+            p->st_bbox_area = (x1 - x0) * (y1 - y0);
         }
         // stations in Morton order: a pipeline stage (kKT consecutive stations) is then a compact
         // blob, so that for Cressman most (cell tile, stage) blocks lie wholly beyond the radius and
@@ -965,8 +1149,10 @@ static int plan_create_impl(ipr_plan** plan, int device, const double* cell_x, c
         IPR_CUDA(cudaMemcpyAsync(p->d_st, hs.data(), sizeof(double2) * hs.size(), cudaMemcpyHostToDevice, p->stream));
         IPR_CUDA(cudaStreamSynchronize(p->stream));  // staging vectors go out of scope
     }
+    tr.mark("(plan) stations sorted and uploaded");
     const int rc = scan_zero_pairs(p, err, errlen);
     if (rc != IPR_OK) return rc;
+    tr.mark("(plan) zero-distance scan done");
     *plan = holder.release();
     return IPR_OK;
 }
@@ -1008,9 +1194,13 @@ void ipr_plan_destroy(ipr_plan* p) {
     dev_free(p->d_n_active);
     dev_free(p->d_perm);
     dev_free(p->d_run_perm);
+    for (auto& kv : p->run_perm_alt) dev_free(kv.second);
     dev_free(p->d_stage_box);
     dev_free(p->d_cell_keep);
     dev_free(p->d_active_total);
+    dev_free(p->d_cr_panel);
+    dev_free(p->d_cr_list);
+    dev_free(p->d_cr_counter);
     for (auto& sp : p->spans) {
         cudaEventDestroy(sp.e0);
         cudaEventDestroy(sp.e1);
@@ -1153,7 +1343,10 @@ static int plan_cressman_impl(ipr_plan* p, const double* radii_m, int32_t n_radi
         WeightParams wp{};
         wp.a = radii_m[ri] * radii_m[ri];
         p->phase_radius = ri;
-        rc = run_contraction(p, kCressman, wp, false, t0, t1, d_out + (size_t)ri * stack_stride, ld_out, err, errlen);
+        if (cressman_legacy())
+            rc = run_contraction(p, kCressman, wp, false, t0, t1, d_out + (size_t)ri * stack_stride, ld_out, err, errlen);
+        else
+            rc = run_cressman_radius(p, radii_m[ri], t0, t1, d_out + (size_t)ri * stack_stride, ld_out, err, errlen);
         p->phase_radius = -1;
         if (rc) return rc;
         if ((rc = run_post(p, t0, t1, d_out + (size_t)ri * stack_stride, ld_out, err, errlen))) return rc;
@@ -1317,7 +1510,16 @@ std::vector<int> parse_cpulist(const char* s) {
 
 // CPUs local to a CUDA device that this process may run on; empty when unknown or when they are all the
 // CPUs anyway (single-node hosts: nothing to bind)
+std::vector<int> device_local_cpus_uncached(int device);
 std::vector<int> device_local_cpus(int device) {
+    static std::mutex mu;
+    static std::map<int, std::vector<int>> cache;   // sysfs + cudaDeviceGetPCIBusId once per device
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(device);
+    if (it == cache.end()) it = cache.emplace(device, device_local_cpus_uncached(device)).first;
+    return it->second;
+}
+std::vector<int> device_local_cpus_uncached(int device) {
     std::vector<int> out;
     if (!numa_enabled()) return out;
     char bdf[32] = "";
@@ -1549,18 +1751,6 @@ private:
     std::vector<int> cpus_;
 };
 
-// IPR_TRACE=1: phase timestamps of the host-buffer path on stderr
-struct Trace {
-    bool on;
-    std::chrono::steady_clock::time_point t0;
-    Trace() : on(getenv("IPR_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
-    void mark(const char* what) {
-        if (!on) return;
-        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        fprintf(stderr, "[ipr trace] %8.2f ms  %s\n", ms, what);
-    }
-};
-
 // One device's share of a host-buffer job: cells [c0, c1) for every date (and every stack).
 int run_device_block(const HostJob& job, int device, long long c0, long long c1, char* err, size_t errlen) {
     if (c0 >= c1) return IPR_OK;
@@ -1625,22 +1815,31 @@ int run_device_block(const HostJob& job, int device, long long c0, long long c1,
     const int n_ring = std::min<int>(kRing, (int)items.size());
     for (int i = 0; i < n_ring; i++) {
         IPR_CUDA(dev_malloc(&g.ring[i], sizeof(double) * slot_doubles));
-        // the host paces itself on these (cancellation and progress are decided per work item)
-        IPR_CUDA(cudaEventCreateWithFlags(&g.done[i], cudaEventDisableTiming | cudaEventBlockingSync));
+        IPR_CUDA(cudaEventCreateWithFlags(&g.done[i], cudaEventDisableTiming));
         IPR_CUDA(cudaEventCreateWithFlags(&g.computed[i], cudaEventDisableTiming));
     }
     tr.mark("ring allocated");
     bool cancelled = false;
     long long reported = 0;
+    // the host polls the slot's event (sleeping 100 us between queries: no interrupt-driven blocking sync on the
+    // copy stream); IPR_PACE=0 queues everything at once behind stream waits (no progress, cancel only at the start)
+    const bool pace_on_host = !(getenv("IPR_PACE") && atoi(getenv("IPR_PACE")) == 0);
     for (size_t ii = 0; ii < items.size(); ii++) {
         const WorkItem& it = items[ii];
         const int slot = (int)(ii % n_ring);
         if ((int)ii >= n_ring) {
             // the slot's previous chunk has reached the host: the GPU still holds the chunks in between, so
             // waiting here on the host costs no bubble, and it is where a job is cancelled / reports progress
-            IPR_CUDA(cudaEventSynchronize(g.done[slot]));
-            if (job.done) job.done->fetch_add(1);
-            reported++;
+            if (pace_on_host) {
+                cudaError_t q;
+                while ((q = cudaEventQuery(g.done[slot])) == cudaErrorNotReady)
+                    std::this_thread::sleep_for(std::chrono::microseconds(100));
+                IPR_CUDA(q);
+                if (job.done) job.done->fetch_add(1);
+                reported++;
+            } else {
+                IPR_CUDA(cudaStreamWaitEvent(plan->stream, g.done[slot], 0));
+            }
         }
         if (job.cancel && job.cancel->load() != 0) {
             cancelled = true;
@@ -1719,9 +1918,10 @@ int run_host_job(const HostJob& job, const int* devices, int n_devices, char* er
         if (e != cudaSuccess) cudaGetLastError();
         jobx.out_pinned = (e == cudaSuccess && attr.type == cudaMemoryTypeHost);
     }
-    if (!jobx.out_pinned && !(getenv("IPR_THP") && atoi(getenv("IPR_THP")) == 0)) {
-        // a fresh pageable result (what R's allocVector returns) is first touched by the staging fan-out: ask
-        // for transparent huge pages so that 29 GB cost ~14 k page faults instead of 7 M (no-op where THP is off)
+    if (!jobx.out_pinned && getenv("IPR_THP") && atoi(getenv("IPR_THP")) != 0) {
+        // opt-in: transparent huge pages for a fresh pageable result.  Measured on the B200 box (THP = madvise,
+        // 29.2 GB never-touched matrix): 1.39 s with the hint against 0.95 s without — zeroing 2 MB pages inside
+        // the fault handler serialises what the 4 KB faults of the 16 staging threads spread out — so it is off
         const size_t bytes = sizeof(double) * (size_t)job.n_cells * job.n_dates * (job.cressman ? job.n_radii : 1);
         const uintptr_t lo = (reinterpret_cast<uintptr_t>(job.out) + 4095) & ~uintptr_t(4095);
         const uintptr_t hi = (reinterpret_cast<uintptr_t>(job.out) + bytes) & ~uintptr_t(4095);

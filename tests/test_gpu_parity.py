@@ -504,7 +504,10 @@ def test_multi_device_scheduler_on_one_gpu(n_dates):
     radii = np.array([4e3, 9e3, 30e3])
     c1 = np.ascontiguousarray(engine.cressman_grid(cx, cy, sx, sy, obs, radii, devices=[0]))
     c3 = np.ascontiguousarray(engine.cressman_grid(cx, cy, sx, sy, obs, radii, devices=[0, 0, 0], n_round=None))
-    assert np.array_equal(c1, c3, equal_nan=True)   # Cressman has a single path: bit-identical
+    # a shard's cell tiles are composed differently, so a cell's station list is padded and grouped into
+    # k-steps differently: the same products, summed in another order
+    assert np.array_equal(np.isnan(c1), np.isnan(c3))
+    assert_parity(c3, c1, tol=1e-12, label="sharded cressman")
     assert_parity(one, ref.idw_reference(cx, cy, sx, sy, obs, 2.0), label="sharded idw")
 
 
@@ -771,8 +774,9 @@ def test_job_api_progress_and_result():
     jobc = engine.Job.cressman(cx, cy, sx, sy, obs, radii, devices=[0, 0])
     fin, done, total = jobc.wait(-1)
     assert fin and done == total == 2 * (2 * 9 + 1)
-    assert np.array_equal(np.ascontiguousarray(jobc.finish()),
-                          np.ascontiguousarray(engine.cressman_grid(cx, cy, sx, sy, obs, radii)), equal_nan=True)
+    # two shards compose their cell tiles differently from one: same products, another order of summation
+    assert_parity(np.ascontiguousarray(jobc.finish()),
+                  np.ascontiguousarray(engine.cressman_grid(cx, cy, sx, sy, obs, radii)), tol=1e-12, label="cressman job")
 
 
 def test_job_cancel_returns_cancelled_and_leaves_the_library_usable():
