@@ -468,10 +468,11 @@ def run_workload(a, wl, ctx):
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
             "traffic": ctx.traffic.get(wl),
-            "kernel": "ipr::contract_kernel<8,false,false,2> (FP64 DMMA.8x8x4, 2 CTAs/SM, 8-station half stages; "
-                      "one launch group per radius)",
-            "flops_counted": "executed: 2*S per cell-day and radius x the fraction of (cell tile, half stage) blocks "
-                             "that hold any non-zero weight; the dense-equivalent rate is in `dense_equivalent_tflops`",
+            "kernel": "ipr::cressman_kernel<8,2> (persistent, 2 CTAs/SM; per cell tile: station list + weights, then "
+                      "gathered-row FP64 DMMA.8x8x4 contraction over all date tiles; one launch per radius)",
+            "flops_counted": "executed: 2 x 8 stations x 64 cells x 128 dates per pipeline stage run (a cell tile's "
+                             "stations within reach, padded to whole stages), as a fraction of the dense 2*S per "
+                             "cell-day and radius; the dense-equivalent rate is in `dense_equivalent_tflops`",
             "executed_block_frac": executed_frac,
             "dense_equivalent_tflops": dense_flops / (kernel_ms * 1e-3) * 1e-12,
             "kernel_ms": kernel_ms,

@@ -79,6 +79,20 @@ int ipr_cressman_f64(const double* cell_x, const double* cell_y, int64_t n_cells
                      const int* devices, int n_devices,
                      double* out, char* err, size_t errlen);
 
+/* Kriging_Ordinary's IDW fallback (first slice): what perform_kriging computes for a date whose
+ * variogram is flat or whose kriging matrix is singular / ill-conditioned (R/Kriging_Ordinary.R:465-476), with
+ * its per-date prelude (:406-423).  Per date, over the stations available on it:
+ *   fewer than two  -> the layer is their mean (0 when there is none)
+ *   all equal       -> the layer is that value
+ *   otherwise       -> sum(w * v) / sum(w), w = 1 / d^2 with d == 0 replaced by 1e-10
+ * Never NA.  The caller passes the dates for which it has chosen the fallback (the choice depends on the fitted
+ * variogram and stays in R); arguments as for ipr_idw_f64. */
+int ipr_idw_kriging_f64(const double* cell_x, const double* cell_y, int64_t n_cells,
+                        const double* st_x, const double* st_y, int32_t n_st,
+                        const double* obs, int32_t n_dates,
+                        const int* devices, int n_devices,
+                        double* out, char* err, size_t errlen);
+
 /* ---------------------------------------------------------------------------------------
  * The same two calls with the reference's next steps fused on the device, so that a large stack
  * needs no further host pass:
@@ -167,6 +181,9 @@ int ipr_plan_set_obs_device(ipr_plan* plan, const double* d_obs, char* err, size
  * d_out + (t - t0) * ld_out, ld_out >= n_cells.  Launches are asynchronous on the plan stream. */
 int ipr_plan_idw(ipr_plan* plan, double p, int32_t t0, int32_t t1,
                  double* d_out, int64_t ld_out, char* err, size_t errlen);
+/* the Kriging fallback rule of ipr_idw_kriging_f64 */
+int ipr_plan_idw_kriging(ipr_plan* plan, int32_t t0, int32_t t1,
+                         double* d_out, int64_t ld_out, char* err, size_t errlen);
 /* radius ri's stack starts at d_out + ri * stack_stride (elements) */
 int ipr_plan_cressman(ipr_plan* plan, const double* radii_m, int32_t n_radii,
                       int32_t t0, int32_t t1, double* d_out, int64_t ld_out,

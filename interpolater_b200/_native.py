@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "ipr_plan_stage_blocks", "ipr_plan_profile", "ipr_plan_profile_read",
     "ipr_plan_stream", "ipr_host_alloc", "ipr_host_free", "ipr_release_cached_memory",
     "ipr_job_start_idw", "ipr_job_start_cressman", "ipr_job_wait", "ipr_job_cancel", "ipr_job_finish",
-    "ipr_cell_split_bounds",
+    "ipr_cell_split_bounds", "ipr_idw_kriging_f64", "ipr_plan_idw_kriging",
 ]
 
 
@@ -66,6 +66,11 @@ def load() -> C.CDLL:
     lib.ipr_idw_f64.restype = C.c_int
     lib.ipr_idw_f64.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, C.c_double,
                                 ip, C.c_int, vp, C.c_char_p, C.c_size_t]
+    lib.ipr_idw_kriging_f64.restype = C.c_int
+    lib.ipr_idw_kriging_f64.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32,
+                                        ip, C.c_int, vp, C.c_char_p, C.c_size_t]
+    lib.ipr_plan_idw_kriging.restype = C.c_int
+    lib.ipr_plan_idw_kriging.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int64, C.c_char_p, C.c_size_t]
     lib.ipr_cressman_f64.restype = C.c_int
     lib.ipr_cressman_f64.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, vp, C.c_int32,
                                      ip, C.c_int, vp, C.c_char_p, C.c_size_t]

@@ -244,6 +244,11 @@ struct ipr_plan {
     double* d_z0 = nullptr;
     double* d_mask = nullptr;
     uint8_t* d_flag = nullptr;
+    // Kriging fallback (ipr_plan_idw_kriging): per-date constant-layer flags and values, built on first use
+    uint8_t* d_kflag = nullptr;
+    double* d_kconst = nullptr;
+    bool kflags_ready = false;
+    std::vector<uint8_t> h_has_na_raw;   // any NA on the date, before the sparse-NA reclassification of IDW()
     uint8_t* d_has_na = nullptr;
     int* d_counters = nullptr;  // [0] zero pairs, [1] non-finite obs
     int2* d_pairs = nullptr;
@@ -345,7 +350,7 @@ struct TileSets {
     std::vector<int> u[9];  // unmasked, NP = 2, 4, 6, 8 used
     std::vector<int> m[5];  // masked,   NP = 2, 4 used
 };
-void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, TileSets& ts);
+void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, TileSets& ts, bool raw_na = false);
 
 template <int NP, bool MASKED, int KSTEPS = kKSteps>
 int launch_contract(ipr_plan* p, ContractArgs& a, const std::vector<int>& tiles, char* err, size_t errlen) {
@@ -444,6 +449,7 @@ int ensure_weights(ipr_plan* p, int mode, const WeightParams& wp, int tile0, int
         case kIdwP2: weights_kernel<kIdwP2><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
         case kIdwEvenP: weights_kernel<kIdwEvenP><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
         case kIdwGenericP: weights_kernel<kIdwGenericP><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
+        case kIdwKriging: weights_kernel<kIdwKriging><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
         default: weights_kernel<kCressman><<<n_tiles, kThreads, 0, p->stream>>>(w); break;
     }
     IPR_CUDA(cudaGetLastError());
@@ -639,10 +645,14 @@ int run_int8_masked(ipr_plan* p, int mode, const WeightParams& wp, ContractArgs&
 // One weight function over the date range: loops over cell-tile chunks of the A-operand cache
 int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int t0, int t1, double* d_out,
                     long long ld_out, char* err, size_t errlen) {
+    // Kriging fallback: a co-located station weighs 1e20, so its absence on a date can neither be subtracted
+    // afterwards (sparse-NA correction) nor sliced into 8-bit digits next to weights 1e-30 times smaller: every
+    // granule with an NA goes through the FP64 masked GEMM
+    const bool krig = (mode == kIdwKriging);
     TileSets ts;
-    build_tiles(p, t0, t1, idw, ts);
+    build_tiles(p, t0, t1, idw, ts, krig);
     const bool masked_here = idw && (!ts.m[4].empty() || !ts.m[2].empty());
-    int rc = ensure_wcache(p, masked_here && p->int8_mask, err, errlen);
+    int rc = ensure_wcache(p, masked_here && p->int8_mask && !krig, err, errlen);
     if (rc) return rc;
     if (mode == kCressman && (rc = ensure_run_perm(p, err, errlen))) return rc;
     const int total_tiles = (int)(p->c_pad / kCellsPerCta);
@@ -657,7 +667,8 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
         a.run_perm = (mode == kCressman) ? p->d_run_perm : nullptr;
         a.z0 = p->d_z0;
         a.mask = p->d_mask;
-        a.date_flag = idw ? p->d_flag : nullptr;
+        a.date_flag = krig ? p->d_kflag : idw ? p->d_flag : nullptr;
+        a.date_const = krig ? p->d_kconst : nullptr;
         a.out = d_out;
         a.ld_out = ld_out;
         a.n_cells = p->n_cells;
@@ -667,7 +678,7 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
         a.t_lo = t0;
         a.t_hi = t1;
         // masked granules through the error-free int8 mask contraction (every chunk of cell tiles)
-        const bool use_int8 = masked_here && p->int8_mask && p->d_wq != nullptr;
+        const bool use_int8 = masked_here && p->int8_mask && p->d_wq != nullptr && !krig;
         if (use_int8 && (rc = run_int8_masked(p, mode, wp, a, ts, t0, t1, err, errlen))) return rc;
         if (mode == kCressman) {   // half stages (8 stations): finer active lists
             constexpr int K = kCressmanKSteps;
@@ -692,12 +703,13 @@ int run_contraction(ipr_plan* p, int mode, const WeightParams& wp, bool idw, int
 // granule with any NA inside the window (when `use_mask`) becomes two masked 64-date tiles, the
 // others one 128-date tile; the width actually computed is trimmed to the window in steps of
 // 32 dates (NP = 2, 4, 6, 8), so the ragged last granule does not pay for empty columns.
-void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, TileSets& ts) {
+void build_tiles(const ipr_plan* p, int t0, int t1, bool use_mask, TileSets& ts, bool raw_na) {
+    const std::vector<uint8_t>& has_na = raw_na ? p->h_has_na_raw : p->h_has_na;
     for (int b = t0 - t0 % kGran; b < t1; b += kGran) {
         const int lo = std::max(b, t0), hi = std::min(b + kGran, t1);
         bool na = false;
         if (use_mask)
-            for (int t = lo; t < hi; t++) na |= (p->h_has_na[t] != 0);
+            for (int t = lo; t < hi; t++) na |= (has_na[t] != 0);
         if (na) {
             for (int h = b; h < b + kGran; h += 64) {
                 if (h >= hi || h + 64 <= lo) continue;
@@ -936,6 +948,8 @@ int prepare_obs(ipr_plan* p, char* err, size_t errlen) {
     // unmasked contraction + denominator correction of the affected dates; otherwise masked GEMM.
     // (regenerating a missing weight costs ~10 FP64 instructions against 1 FMA per entry of the
     // masked GEMM, so the break-even is near 10 % NA.)
+    p->h_has_na_raw = p->h_has_na;
+    p->kflags_ready = false;
     p->h_date_mode.assign(p->n_dates, 0);
     p->any_sparse_fix = false;
     const bool allow_sparse = !(getenv("IPR_SPARSE_NA") && atoi(getenv("IPR_SPARSE_NA")) == 0);
@@ -1174,6 +1188,8 @@ void ipr_plan_destroy(ipr_plan* p) {
     dev_free(p->d_z0);
     dev_free(p->d_mask);
     dev_free(p->d_flag);
+    dev_free(p->d_kflag);
+    dev_free(p->d_kconst);
     dev_free(p->d_has_na);
     dev_free(p->d_na_n);
     dev_free(p->d_na_idx);
@@ -1297,6 +1313,36 @@ static int plan_idw_impl(ipr_plan* p, double pw, int32_t t0, int32_t t1, double*
 int ipr_plan_idw(ipr_plan* p, double pw, int32_t t0, int32_t t1, double* d_out, int64_t ld_out, char* err,
                  size_t errlen) {
     return no_throw(err, errlen, [&] { return plan_idw_impl(p, pw, t0, t1, d_out, ld_out, err, errlen); });
+}
+
+// Kriging_Ordinary's IDW fallback over [t0, t1): R/Kriging_Ordinary.R:406-423 (constant layers) and :465-476
+// (the weighted mean with d == 0 -> 1e-10).  Same contraction as IDW(); no zero-distance running mean, no
+// early-out on all-zero dates, never NA.
+static int plan_idw_kriging_impl(ipr_plan* p, int32_t t0, int32_t t1, double* d_out, int64_t ld_out, char* err,
+                                 size_t errlen) {
+    int rc = check_range(p, t0, t1, d_out, ld_out, err, errlen);
+    if (rc) return rc;
+    if (t0 == t1) return IPR_OK;
+    IPR_CUDA(cudaSetDevice(p->device));
+    if (!p->kflags_ready) {
+        if (!p->d_kflag) {
+            IPR_CUDA(dev_malloc(&p->d_kflag, (size_t)p->n_gran * kGran));
+            IPR_CUDA(dev_malloc(&p->d_kconst, sizeof(double) * (size_t)p->n_gran * kGran));
+        }
+        PhaseScope ps(p, IPR_PHASE_PREP);
+        kriging_flags_kernel<<<(p->n_dates + 7) / 8, 256, 0, p->stream>>>(p->d_obs, p->n_dates, p->n_dates, p->n_st,
+                                                                         p->d_kflag, p->d_kconst);
+        IPR_CUDA(cudaGetLastError());
+        p->launches++;
+        p->kflags_ready = true;
+    }
+    WeightParams wp{};
+    if ((rc = run_contraction(p, kIdwKriging, wp, true, t0, t1, d_out, ld_out, err, errlen))) return rc;
+    return run_post(p, t0, t1, d_out, ld_out, err, errlen);
+}
+
+int ipr_plan_idw_kriging(ipr_plan* p, int32_t t0, int32_t t1, double* d_out, int64_t ld_out, char* err, size_t errlen) {
+    return no_throw(err, errlen, [&] { return plan_idw_kriging_impl(p, t0, t1, d_out, ld_out, err, errlen); });
 }
 
 int ipr_plan_set_post(ipr_plan* p, int32_t round_mode, int32_t n_round, const uint8_t* cell_keep, char* err,
@@ -1449,6 +1495,7 @@ struct HostJob {
     bool out_pinned = false;  // caller's output is page-locked: D2H lands in it directly
     int round_mode = 0, n_round = 0;
     const uint8_t* cell_keep = nullptr;
+    bool kriging = false;                         // IDW fallback of Kriging_Ordinary instead of IDW()
     int n_job_devices = 1;                        // devices sharing the host's cores / memory bandwidth in this job
     // asynchronous jobs (ipr_job_*): cooperative cancellation and progress in work items (date chunks)
     std::atomic<int>* cancel = nullptr;
@@ -1848,7 +1895,8 @@ int run_device_block(const HostJob& job, int device, long long c0, long long c1,
         if (job.cressman)
             rc = ipr_plan_cressman(plan, job.radii + it.stack, 1, it.t0, it.t1, g.ring[slot], nc, 0, err, errlen);
         else
-            rc = ipr_plan_idw(plan, job.p, it.t0, it.t1, g.ring[slot], nc, err, errlen);
+            rc = job.kriging ? ipr_plan_idw_kriging(plan, it.t0, it.t1, g.ring[slot], nc, err, errlen)
+                             : ipr_plan_idw(plan, job.p, it.t0, it.t1, g.ring[slot], nc, err, errlen);
         if (rc) return rc;
         IPR_CUDA(cudaEventRecord(g.computed[slot], plan->stream));
         IPR_CUDA(cudaStreamWaitEvent(g.copy, g.computed[slot], 0));
@@ -2084,6 +2132,14 @@ int ipr_idw_f64(const double* cell_x, const double* cell_y, int64_t n_cells, con
                 int32_t n_st, const double* obs, int32_t n_dates, double p, const int* devices, int n_devices,
                 double* out, char* err, size_t errlen) {
     HostJob job{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, false, p, nullptr, 0, out};
+    return no_throw(err, errlen, [&] { return run_host_job(job, devices, n_devices, err, errlen); });
+}
+
+int ipr_idw_kriging_f64(const double* cell_x, const double* cell_y, int64_t n_cells, const double* st_x,
+                        const double* st_y, int32_t n_st, const double* obs, int32_t n_dates, const int* devices,
+                        int n_devices, double* out, char* err, size_t errlen) {
+    HostJob job{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, false, 2.0, nullptr, 0, out};
+    job.kriging = true;
     return no_throw(err, errlen, [&] { return run_host_job(job, devices, n_devices, err, errlen); });
 }
 

@@ -64,7 +64,8 @@ enum WeightMode : int {
     kIdwP2 = 0,       // w = 1/d^2
     kIdwEvenP = 1,    // w = (1/d^2)^n, p = 2n
     kIdwGenericP = 2, // w = pow(d^2, -p/2)
-    kCressman = 3     // w = (R^2 - d^2)/(R^2 + d^2), 0 when d^2 > R^2
+    kCressman = 3,    // w = (R^2 - d^2)/(R^2 + d^2), 0 when d^2 > R^2
+    kIdwKriging = 4   // Kriging_Ordinary's IDW fallback: w = 1/d^2 with d == 0 replaced by 1e-10 (no fix-up)
 };
 
 struct WeightParams {
@@ -87,7 +88,9 @@ struct ContractArgs {
                               // of run run_perm[8T + w] (spatially compact tiles for Cressman)
     const double* z0;         // granule blocks [n_gran][n_stages][kBlkDoubles]
     const double* mask;       // same layout (masked variants only)
-    const uint8_t* date_flag; // IDW: 0 normal, 1 all-NA layer, 2 exact-zero layer; nullptr for Cressman
+    const uint8_t* date_flag; // IDW: 0 normal, 1 all-NA layer, 2 exact-zero layer, 3 constant layer date_const[t]
+                              // (Kriging fallback); nullptr for Cressman
+    const double* date_const; // [n_dates] value of the flag-3 layers, or nullptr
     double* out;              // layer t at out + (t - t_lo) * ld_out
     long long ld_out;
     long long n_cells;
@@ -187,7 +190,10 @@ __device__ __forceinline__ double weight_from_d2(double d2, const WeightParams& 
         // R/IDW.R:310-326.  The test is on the bit pattern so it stays off the FP64 pipe.
         const bool zero = ((__double2hiint(d2) | __double2loint(d2)) == 0);
         double w;
-        if (WMODE == kIdwP2) {
+        if (WMODE == kIdwKriging) {
+            // R/Kriging_Ordinary.R:470-471: distances[distances == 0] <- 1e-10; weights <- 1 / distances^2
+            return rcp_nr2(zero ? 1e-10 * 1e-10 : d2);
+        } else if (WMODE == kIdwP2) {
             w = rcp_nr2(d2);
         } else if (WMODE == kIdwEvenP) {
             const double r = rcp_nr2(d2);
@@ -491,6 +497,7 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
                 const uint8_t fl = args.date_flag[t];
                 if (fl == 1) v = na;        // R/IDW.R:299-301 all-NA date
                 else if (fl == 2) v = 0.0;  // R/IDW.R:294-297 all |obs| < 1e-12
+                else if (fl == 3) v = args.date_const[t];   // R/Kriging_Ordinary.R:410-423 constant layer
             }
             // streaming store: the output is written once and never re-read by this kernel, so it must
             // not displace the L2-resident B operand and the A tiles shared by concurrent CTAs
@@ -873,6 +880,39 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
     }
     if (IPR_CR_PROFILE && args.prof && lane == 0)
         for (int i = 0; i < 8; i++) atomicAdd(args.prof + i, (unsigned long long)pf[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kriging_Ordinary's per-date prelude (R/Kriging_Ordinary.R:406-423): fewer than two available stations ->
+// the layer is their mean (or 0 when there is none); all available values equal -> that value.  One warp
+// per date; flag 3 + the constant, else flag 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void kriging_flags_kernel(const double* __restrict__ obs, long long ld_obs, int n_dates, int n_st,
+                                     uint8_t* __restrict__ flag, double* __restrict__ value) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= n_dates) return;
+    int cnt = 0;
+    double lo = 1e308 * 10.0, hi = -1e308 * 10.0;   // +inf / -inf
+    for (int s = lane; s < n_st; s += 32) {
+        const double v = obs[(long long)s * ld_obs + t];
+        if (v == v) {
+            cnt++;
+            lo = fmin(lo, v);
+            hi = fmax(hi, v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+        const bool constant = (cnt < 2) || (lo == hi);
+        flag[t] = constant ? 3 : 0;
+        value[t] = (cnt == 0) ? 0.0 : lo;   // one station: its value is the mean; all equal: the value
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

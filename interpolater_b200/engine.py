@@ -80,6 +80,29 @@ def idw_grid(cell_x, cell_y, st_x, st_y, obs, p=2.0, devices=None, out=None, n_r
     return out
 
 
+def idw_kriging_fallback_grid(cell_x, cell_y, st_x, st_y, obs, devices=None, out=None):
+    """The IDW fallback of Kriging_Ordinary's perform_kriging (R/Kriging_Ordinary.R:406-423, :465-476) over every
+    cell x date: constant layers for dates with fewer than two (or only equal) available values, otherwise the
+    inverse-square-distance mean with d == 0 -> 1e-10.  Returns (n_cells, n_dates) float64, Fortran order."""
+    lib = _native.load()
+    cx, cy = _f64(cell_x, "cell_x"), _f64(cell_y, "cell_y")
+    sx, sy = _f64(st_x, "st_x"), _f64(st_y, "st_y")
+    if cx.shape != cy.shape or sx.shape != sy.shape:
+        raise ValueError("coordinate arrays must have matching lengths")
+    ob = _obs_colmajor(obs, sx.shape[0])
+    n_dates = ob.shape[0]
+    if out is None:
+        out = np.empty((cx.shape[0], n_dates), dtype=np.float64, order="F")
+    elif out.shape != (cx.shape[0], n_dates) or not out.flags.f_contiguous or out.dtype != np.float64:
+        raise ValueError("out must be a Fortran-ordered float64 (n_cells, n_dates) array")
+    dev, ndev = _devices(devices)
+    err = _native.errbuf()
+    rc = lib.ipr_idw_kriging_f64(cx.ctypes.data, cy.ctypes.data, cx.shape[0], sx.ctypes.data, sy.ctypes.data,
+                                 sx.shape[0], ob.ctypes.data, n_dates, dev, ndev, out.ctypes.data, err, _native.ERRLEN)
+    _native.check(rc, err)
+    return out
+
+
 def cressman_grid(cell_x, cell_y, st_x, st_y, obs, radii_m, devices=None, out=None, n_round=None,
                   round_mode=ROUND_TERRA, cell_keep=None):
     """Cressman analysis for each radius (metres, ascending unique).  Returns

@@ -148,6 +148,44 @@ def idw_reference(cx, cy, sx, sy, obs, p=2.0):
 #: rowSums accumulates in long double in R; emulating that in NumPy costs an extra widened copy.
 #: bench.py's CPU-baseline leg sets this to False (plain float64 pairwise sums, ~1e-16 apart) so
 #: that the timed port is not slower than R's C loop would be.
+# --------------------------------------------------------------------------------------
+# Kriging_Ordinary: the IDW fallback of perform_kriging and its per-date prelude
+# --------------------------------------------------------------------------------------
+def kriging_idw_fallback_one_date(dist_pred_obs, obs_vec):
+    """One date of perform_kriging when `use_idw` is TRUE (flat variogram, or a singular / ill-conditioned
+    gamma matrix), R/Kriging_Ordinary.R:405-423 and :465-476:
+
+        available_values <- obs_values[!is.na(obs_values)]
+        if (length(available_stations) < 2)  value = mean(available_values), or 0 when there is none
+        if (length(unique(available_values)) == 1)  value = that value
+        distances[distances == 0] <- 1e-10 ; weights <- 1 / (distances^2)
+        sum(weights * available_values) / sum(weights)
+
+    dist_pred_obs is the cell x station distance matrix (terra::distance, :399-402)."""
+    obs_vec = np.asarray(obs_vec, dtype=np.float64)
+    avail = ~_is_na(obs_vec)
+    vals = obs_vec[avail]
+    n_cells = dist_pred_obs.shape[0]
+    if vals.size < 2:                                             # :410-417
+        return np.full(n_cells, float(vals.mean()) if vals.size > 0 else 0.0)
+    if np.unique(vals).size == 1:                                 # :420-423
+        return np.full(n_cells, float(vals[0]))
+    d = dist_pred_obs[:, avail].copy()
+    d[d == 0] = 1e-10                                             # :470
+    w = 1.0 / (d * d)                                             # :471 (R evaluates x^2 as x * x)
+    return (w * vals[None, :]).sum(axis=1) / w.sum(axis=1)       # :472
+
+
+def kriging_idw_fallback_reference(cx, cy, sx, sy, obs):
+    """All dates of `obs` (n_dates x n_stations) through kriging_idw_fallback_one_date; (n_cells, n_dates)."""
+    dist = distance_matrix(cx, cy, sx, sy)
+    obs = np.asarray(obs, dtype=np.float64)
+    out = np.empty((dist.shape[0], obs.shape[0]), dtype=np.float64, order="F")
+    for t in range(obs.shape[0]):
+        out[:, t] = kriging_idw_fallback_one_date(dist, obs[t])
+    return out
+
+
 LONG_DOUBLE_ROWSUMS = True
 
 

@@ -806,3 +806,46 @@ def test_more_than_65535_colocated_cells():
         ok = ~np.isnan(obs[t])
         assert np.array_equal(got[cells[ok], t], obs[t, ok])
     assert not np.isnan(got).any()
+
+
+# ---------------------------------------------------------------- Kriging_Ordinary's IDW fallback
+@pytest.mark.parametrize("shape", [(40, 30, 60, 300), (9, 7, 11, 12), (5, 3, 2, 4), (33, 20, 140, 700)])
+def test_kriging_idw_fallback_matches_oracle(shape):
+    """ipr_idw_kriging_f64 against R/Kriging_Ordinary.R:406-423, :465-476 as restated by the oracle: NA-free and
+    NA-bearing granules (FP64 masked GEMM), co-located stations (weight 1e20, present and absent), dates with
+    none / one / only equal available values."""
+    ncol, nrow, n_st, n_dates = shape
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(ncol, nrow, n_st, n_dates, na_frac=0.2,
+                                                   plant_zero_dist=min(3, n_st), seed=n_st)
+    obs[0, :] = np.nan
+    obs[1, :] = np.nan
+    obs[1, n_st // 2] = 4.75
+    obs[2, :] = np.where(np.isnan(obs[2, :]), np.nan, 1.5)
+    if n_dates > 140:
+        obs[140:, :] = np.where(np.isnan(obs[140:, :]), 0.3, obs[140:, :])   # NA-free granules: unmasked tiles
+    got = engine.idw_kriging_fallback_grid(cx, cy, sx, sy, obs)
+    want = ref.kriging_idw_fallback_reference(cx, cy, sx, sy, obs)
+    assert not np.isnan(got).any()
+    assert_parity(got, want, label=f"kriging fallback {shape}")
+    assert np.all(got[:, 0] == 0.0) and np.all(got[:, 1] == 4.75)
+    if np.unique(obs[2][~np.isnan(obs[2])]).size == 1:
+        assert np.all(got[:, 2] == 1.5)
+
+
+def test_kriging_idw_fallback_differs_from_idw_only_where_the_rules_differ():
+    """Same contraction as IDW(): away from co-located stations and special dates the two agree to rounding."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(30, 20, 40, 200, na_frac=0.1, seed=5)
+    obs = np.where(np.abs(obs) < 1e-12, 0.7, obs)            # no all-zero dates, no constant dates
+    a = engine.idw_grid(cx, cy, sx, sy, obs, p=2.0)
+    b = engine.idw_kriging_fallback_grid(cx, cy, sx, sy, obs)
+    assert_parity(b, a, tol=1e-12, label="kriging fallback vs IDW away from the special cases")
+
+
+def test_kriging_idw_fallback_multi_shard_and_after_idw():
+    """The fallback through the cell-split scheduler, on a plan cache that held IDW weights just before."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(25, 20, 45, 150, na_frac=0.05, plant_zero_dist=2, seed=8)
+    engine.idw_grid(cx, cy, sx, sy, obs)
+    one = engine.idw_kriging_fallback_grid(cx, cy, sx, sy, obs, devices=[0])
+    many = engine.idw_kriging_fallback_grid(cx, cy, sx, sy, obs, devices=[0, 0, 0])
+    assert_parity(many, one, tol=1e-12, label="kriging fallback shards")
+    assert_parity(one, ref.kriging_idw_fallback_reference(cx, cy, sx, sy, obs), label="kriging fallback")

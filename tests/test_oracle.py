@@ -225,3 +225,48 @@ def test_matrix_form_equals_literal_per_date_loop():
         assert np.array_equal(np.isnan(a), np.isnan(b))
         m = ~np.isnan(a)
         assert np.allclose(a[m], b[m], rtol=1e-12, atol=1e-300)
+
+
+# ---------------------------------------------------------------- Kriging_Ordinary's IDW fallback
+def _kriging_case(seed, n_dates=12):
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(9, 7, 11, n_dates, na_frac=0.25, plant_zero_dist=2, seed=seed)
+    obs[1, :] = np.nan                         # no station available -> 0
+    obs[2, :] = np.nan
+    obs[2, 4] = 6.5                            # one station -> its value
+    obs[3, :] = np.where(np.isnan(obs[3, :]), np.nan, 2.25)   # all available equal -> that value
+    return cx, cy, sx, sy, obs
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_kriging_fallback_oracle_rules(seed):
+    """R/Kriging_Ordinary.R:406-423 (prelude) and :465-476 (weighted mean, d == 0 -> 1e-10), against a scalar
+    per-cell restatement written independently of the vectorised one."""
+    cx, cy, sx, sy, obs = _kriging_case(seed)
+    got = ref.kriging_idw_fallback_reference(cx, cy, sx, sy, obs)
+    assert not np.isnan(got).any()             # the fallback never yields NA
+    assert np.all(got[:, 1] == 0.0) and np.all(got[:, 2] == 6.5) and np.all(got[:, 3] == 2.25)
+    for t in range(obs.shape[0]):
+        v = obs[t]
+        ok = ~np.isnan(v)
+        if ok.sum() < 2 or np.unique(v[ok]).size == 1:
+            continue
+        for c in (0, 17, cx.size - 1):
+            num = den = 0.0
+            for s in np.flatnonzero(ok):
+                d = math.sqrt((cx[c] - sx[s]) ** 2 + (cy[c] - sy[s]) ** 2)
+                if d == 0:
+                    d = 1e-10
+                w = 1.0 / (d * d)
+                num += w * v[s]
+                den += w
+            assert abs(got[c, t] - num / den) <= 1e-12 * max(abs(num / den), 1e-12)
+    # a cell that coincides with an available station takes (to 1e-20 relative) that station's value,
+    # not IDW()'s running mean, and a convex combination stays within the range of the available values
+    t = 5
+    ok = ~np.isnan(obs[t])
+    lo, hi = obs[t][ok].min(), obs[t][ok].max()
+    assert np.all(got[:, t] >= lo - 1e-9) and np.all(got[:, t] <= hi + 1e-9)
+    for s in (0, 1):
+        if ok[s]:
+            c = int(np.flatnonzero((cx == sx[s]) & (cy == sy[s]))[0])
+            assert abs(got[c, t] - obs[t, s]) <= 1e-12 * max(abs(obs[t, s]), 1.0)
