@@ -8,9 +8,24 @@ typedef struct SEXPREC* SEXP;
 typedef ptrdiff_t R_xlen_t;
 typedef unsigned int SEXPTYPE;
 typedef enum { FALSE = 0, TRUE } Rboolean;
+#define CLOSXP 3
+#define LGLSXP 10
 #define INTSXP 13
 #define REALSXP 14
+#define LANGSXP 6
 extern SEXP R_NilValue;
+extern SEXP R_GlobalEnv;
+extern SEXP R_DimSymbol;
+struct R_allocator;
+Rboolean Rf_isFunction(SEXP);
+int Rf_asLogical(SEXP);
+SEXP Rf_allocVector3(SEXPTYPE, R_xlen_t, struct R_allocator*);
+SEXP Rf_setAttrib(SEXP, SEXP, SEXP);
+SEXP Rf_ScalarReal(double);
+SEXP Rf_lang3(SEXP, SEXP, SEXP);
+SEXP R_tryEval(SEXP, SEXP, int*);
+Rboolean R_ToplevelExec(void (*fun)(void*), void* data);
+void R_CheckUserInterrupt(void);
 Rboolean Rf_isReal(SEXP);
 Rboolean Rf_isInteger(SEXP);
 Rboolean Rf_isNull(SEXP);
@@ -38,6 +53,12 @@ void Rf_error(const char*, ...) __attribute__((noreturn));
 #define allocMatrix Rf_allocMatrix
 #define allocVector Rf_allocVector
 #define allocArray Rf_allocArray
+#define isFunction Rf_isFunction
+#define asLogical Rf_asLogical
+#define allocVector3 Rf_allocVector3
+#define setAttrib Rf_setAttrib
+#define ScalarReal Rf_ScalarReal
+#define lang3 Rf_lang3
 #define PROTECT(s) Rf_protect(s)
 #define UNPROTECT(n) Rf_unprotect(n)
 #define error Rf_error

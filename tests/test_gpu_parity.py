@@ -724,7 +724,7 @@ def test_full_size_cfg5_through_the_drop_in_signature():
 def test_all_visible_gpus_equal_one_device():
     """The product entry point over every visible GPU (one process, a host thread + plan per device, each
     device writing its column range of the caller's matrix) against the one-device run: same cells, same
-    arithmetic -> bit-equal for Cressman (one code path), equal to summation order for IDW."""
+    arithmetic -> equal to summation order."""
     import torch
 
     n = torch.cuda.device_count()
@@ -743,7 +743,8 @@ def test_all_visible_gpus_equal_one_device():
     radii = np.array([6e3, 25e3, 90e3])
     c1 = np.ascontiguousarray(engine.cressman_grid(cx, cy, sx, sy, obs, radii, devices=[0]))
     cn = np.ascontiguousarray(engine.cressman_grid(cx, cy, sx, sy, obs, radii, devices=devs))
-    assert np.array_equal(c1, cn, equal_nan=True)
+    # a shard composes its cell tiles (hence each station list's padding and k-step grouping) differently
+    assert_parity(cn, c1, tol=1e-12, label=f"Cressman on devices {devs}")
     # pinned caller buffer: cudaMemcpy2DAsync straight into the column ranges
     lib = _native.load()
     import ctypes as Ct

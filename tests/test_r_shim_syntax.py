@@ -23,14 +23,19 @@ def test_r_shim_compiles_against_mock_r_api():
 def test_r_helper_calls_registered_routines():
     shim = open(os.path.join(ROOT, "r-package", "src", "r_shim.c")).read()
     registered = dict(re.findall(r'\{"(C_ipr_\w+)",\s*\(DL_FUNC\)&\w+,\s*(\d+)\}', shim))
-    assert set(registered) == {"C_ipr_idw", "C_ipr_cressman"}
+    assert registered == {"C_ipr_idw": "9", "C_ipr_cressman": "9", "C_ipr_idw_kriging": "8", "C_ipr_release": "0"}
     helper = open(os.path.join(ROOT, "r-package", "R", "ipr_core.R")).read()
-    for name, nargs in registered.items():
-        m = re.search(r"\.Call\(%s,(.*?)\n\s*if \(is\.null\(devices\)\)" % name, helper, flags=re.S)
-        assert m, f"{name} is not called from ipr_core.R"
-        # arguments before the trailing `devices` expression
-        args = [a for a in re.split(r",(?![^()]*\))", m.group(1)) if a.strip()]
-        assert len(args) + 1 == int(nargs), (name, args)
+    helper_code = "\n".join(l.split("#")[0] for l in helper.splitlines())
+    calls = re.findall(r"\.Call\((C_ipr_\w+)((?:[^()]|\((?:[^()]|\([^()]*\))*\))*)\)", helper_code)
+    assert {c[0] for c in calls} == set(registered), "every registered routine is called from ipr_core.R"
+    for name, rest in calls:
+        # top-level commas of the argument list = number of arguments after the routine symbol
+        depth, n = 0, 0
+        for ch in rest:
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            n += (ch == "," and depth == 0)
+        assert n == int(registered[name]), (name, n, rest)
     # balanced delimiters (cheap guard against a truncated edit; R itself is not available)
     for o, c in ("()", "{}", "[]"):
-        assert helper.count(o) == helper.count(c)
+        assert helper_code.count(o) == helper_code.count(c)
