@@ -128,7 +128,7 @@ def IDW(BD_Obs, BD_Coord, shapefile, grid_resolution, p=2, Mask=True, n_round=No
             sim_pts[inside] = engine.idw_grid(cell_x[cells[inside]], cell_y[cells[inside]], sx, sy, obs, p=float(p),
                                               devices=devices, n_round=nr, round_mode=engine.ROUND_R)
         final_results = validate(tc, data_val["test_data"], None, Rain_threshold, sim_pts=sim_pts, layer_names=labels)
-    if Mask is True:
+    if isinstance(Mask, (bool, np.bool_)) and bool(Mask):   # isTRUE(Mask), R/IDW.R:376
         sub, sub_cells = geom.crop_window(shapefile)
         keep = sub.polygon_cover(shapefile)
         values = engine.idw_grid(cell_x[sub_cells], cell_y[sub_cells], sx, sy, obs, p=float(p), devices=devices,

@@ -474,26 +474,33 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
     if (cell >= args.n_cells) return;
     const double wsum = args.wsum[cell];
     const double inv_wsum = 1.0 / wsum;
+    // thread holds dates tile_t0 + 16 i + 4 q + {0,1,2,3} for its cell:
+    //   frag 2i   -> dates +0 (c0), +2 (c1);  frag 2i+1 -> dates +1 (c0), +3 (c1)
+    // Running pointers and a tile-level bounds test: the per-element form (bounds test, 64-bit multiply) was ~25
+    // dependent instructions per store (measured on cressman_kernel, where it was 72 % of the 25 km launch).
+    const long long ld = args.ld_out;
+    double* pe = args.out + (long long)(tile_t0 - args.t_lo + 4 * q) * ld + cell;
+    const bool whole = tile_t0 >= args.t_lo && tile_t0 + 16 * NP <= args.t_hi;
 #pragma unroll
     for (int i = 0; i < NP; i++) {
-        // thread holds dates tile_t0 + 16 i + 4 q + {0,1,2,3} for its cell:
-        //   frag 2i   -> dates +0 (c0), +2 (c1);  frag 2i+1 -> dates +1 (c0), +3 (c1)
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const int t = tile_t0 + 16 * i + 4 * q + e;
-            if (t < args.t_lo || t >= args.t_hi) continue;
+            const bool in_window = whole || (t >= args.t_lo && t < args.t_hi);
             const int f = 2 * i + (e & 1);
             const int c = e >> 1;
             const double numer = acc[f][c];
-            double* optr = &args.out[(long long)(t - args.t_lo) * args.ld_out + cell];
+            double* optr = pe + e * ld;
             // DENOM_IN_OUT: the per-date denominator was left in the output buffer by
             // denom_umma_kernel (error-free int8 mask contraction) and is replaced by the result
-            const double denom = MASKED ? accm[f][c] : (DENOM_IN_OUT ? *optr : wsum);
+            double denom = wsum;
+            if (MASKED) denom = accm[f][c];
+            else if (DENOM_IN_OUT) denom = in_window ? *optr : 1.0;
             // date-independent denominator: one true division per thread (inv_wsum), then multiplies
             double v = (MASKED || DENOM_IN_OUT) ? numer / denom : numer * inv_wsum;
             // R/IDW.R:332,339 ; R/Cressman.R:317 : !is.finite(v) | denom == 0 -> NA
-            if (!isfinite(v) || denom == 0.0) v = na;
-            if (args.date_flag != nullptr) {
+            v = (isfinite(v) && denom != 0.0) ? v : na;
+            if (args.date_flag != nullptr && in_window) {
                 const uint8_t fl = args.date_flag[t];
                 if (fl == 1) v = na;        // R/IDW.R:299-301 all-NA date
                 else if (fl == 2) v = 0.0;  // R/IDW.R:294-297 all |obs| < 1e-12
@@ -501,8 +508,9 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
             }
             // streaming store: the output is written once and never re-read by this kernel, so it must
             // not displace the L2-resident B operand and the A tiles shared by concurrent CTAs
-            __stcs(optr, v);
+            if (in_window) __stcs(optr, v);
         }
+        pe += 16 * ld;
     }
 }
 
@@ -521,12 +529,15 @@ __global__ void __launch_bounds__(kThreads, 2) contract_kernel(const ContractArg
 //             ill-conditioned weights next to the cut-off are the reference's bit for bit — and parked
 //             in a per-CTA scratch that stays L2-resident (296 CTAs x <= 140 KB);
 //   contract  the B operand of a stage is GATHERED: eight listed station rows (128 dates = 1056 B each,
-//             contiguous in the granule-block layout) by eight bulk copies, through the same mbarrier
-//             pipeline as contract_kernel, which keeps running across the date tiles of the cell tile,
-//             so that the next tile's rows arrive under the current tile's epilogue stores.
-// Against the round-1 path (Morton-blob half stages, one CTA per (cell tile, date tile), one weights pass
-// per radius) this executes 1.05x instead of 1.4-3x the in-range products, removes 450,000 CTA
-// lifecycles per radius, and has no separate weights pass at all.
+//             contiguous in the granule-block layout) by 16-byte cp.async (LDGSTS), landing on the slot's `full`
+//             mbarrier; the pipeline keeps running across the date tiles of the cell tile, so that the next
+//             tile's rows arrive under the current tile's epilogue stores.  A slot is released by one
+//             mbarrier.arrive per warp on its `empty` barrier and refilled by the warp whose turn it is
+//             (rotating duty), kLag stages after its release.
+// Cell tiles are handed out by an atomic counter (dynamic scheduling), their shape (8 x 8 ... 1 x 64 cells) is
+// the host's choice per radius (run_perm).  Against the round-1 path (Morton-blob half stages, one CTA per
+// (cell tile, date tile), one weights pass per radius) this executes 1.05x instead of 1.4-3x the in-range
+// products, removes 450,000 CTA lifecycles per radius, and has no separate weights pass at all.
 // ---------------------------------------------------------------------------------------------
 struct CressmanArgs {
     const double2* cell_xy;      // [c_pad]
@@ -542,7 +553,7 @@ struct CressmanArgs {
     int t_lo, t_hi;
     double* panel;               // per CTA: list_cap * 64 doubles
     int* list;                   // per CTA: list_cap ints
-    int list_cap;                // round_up(n_st, 8)
+    int list_cap;                // round_up(n_st, kCrListPad)
     unsigned long long* active_total;   // += 8-station stages executed per (cell tile)
     int* tile_counter;           // zeroed before the launch: cell tiles are handed out in order, one atomic each
     unsigned long long* prof;    // debugging (IPR_CR_PROF=1): cycles per phase summed over warps, else nullptr
@@ -556,6 +567,9 @@ constexpr int kCrRowBytes = kGranLd * 8;               // 1056
 constexpr int kCrListPad = 16;                         // list capacity granule (the larger stage)
 #ifndef IPR_CR_PROFILE
 #define IPR_CR_PROFILE 0   // 1: per-phase cycle counters in cressman_kernel (IPR_CR_PROF=1 prints them); costs registers
+#endif
+#ifndef IPR_CR_APREF
+#define IPR_CR_APREF 1     // A fragments fetched this many stages ahead of their use (registers)
 #endif
 #ifndef IPR_CR_STAGES2
 #define IPR_CR_STAGES2 12
@@ -783,9 +797,17 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
             for (int lin = 0; lin < kStages && lin < total; lin++) produce(lin);
 
         double w_cur[kCrKSteps];
+#if IPR_CR_APREF == 2
+        double w_nx1[kCrKSteps];
+#endif
         if (ns > 0) {
 #pragma unroll
             for (int kk = 0; kk < kCrKSteps; kk++) w_cur[kk] = panel[(size_t)kk * kThreads];
+#if IPR_CR_APREF == 2
+            const int i1 = (ns > 1) ? 1 : 0;
+#pragma unroll
+            for (int kk = 0; kk < kCrKSteps; kk++) w_nx1[kk] = panel[(size_t)(i1 * kCrKSteps + kk) * kThreads];
+#endif
         }
         const double inv_wsum = 1.0 / wsum;
         if (IPR_CR_PROFILE && args.prof) { const long long t = clock64(); pf[0] += t - pt0; pt0 = t; }
@@ -804,7 +826,13 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
                 const double* zs = reinterpret_cast<const double*>(smem + slot * L::kStageBytes);
                 double w_next[kCrKSteps];
                 {
+#if IPR_CR_APREF == 2
+                    int in = i + 2;                              // wraps into the next date tile (same panel)
+                    if (in >= ns) in -= ns;
+                    if (in >= ns) in -= ns;
+#else
                     const int in = (i + 1 < ns) ? i + 1 : 0;     // the first stage of the next date tile
+#endif
 #pragma unroll
                     for (int kk = 0; kk < kCrKSteps; kk++) w_next[kk] = panel[(size_t)(in * kCrKSteps + kk) * kThreads];
                 }
@@ -838,7 +866,14 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
                 if (IPR_CR_PROFILE && args.prof) { const long long t = clock64(); pf[3] += t - pt0; pt0 = t; }
                 if (lane == 0) mbar_arrive(&empty_bar[slot]);   // this warp's reads of the slot are done (release)
 #pragma unroll
-                for (int kk = 0; kk < kCrKSteps; kk++) w_cur[kk] = w_next[kk];
+                for (int kk = 0; kk < kCrKSteps; kk++) {
+#if IPR_CR_APREF == 2
+                    w_cur[kk] = w_nx1[kk];
+                    w_nx1[kk] = w_next[kk];
+#else
+                    w_cur[kk] = w_next[kk];
+#endif
+                }
                 if (IPR_CR_PROFILE && args.prof) { const long long t = clock64(); pf[4] += t - pt0; pt0 = t; }
             }
             // ---- epilogue of this date tile: normalise, NA rule (R/Cressman.R:316-317), store ----

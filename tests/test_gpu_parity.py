@@ -103,6 +103,34 @@ def test_cressman_matches_oracle(radii_km):
     assert np.all((big == 0.0) | np.isnan(big))
 
 
+@pytest.mark.parametrize("xdiv", ["1", "4", "16", "64"])
+def test_cressman_every_cell_tile_shape_matches_oracle(monkeypatch, xdiv):
+    """The four cell-tile shapes of the fused kernel (8 x 8, 4 x 16, 2 x 32, 1 x 64 cells; chosen per radius in
+    production) forced in turn, on a grid whose width is no multiple of a run and with long and short lists,
+    duplicate-free ragged date range (NP = 6 tail) included; and the round-1 path behind IPR_CRESSMAN_LEGACY."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(83, 37, 150, 330, na_frac=0.07, all_na_dates=(9,), seed=int(xdiv))
+    radii = ref.cressman_radii_m([2, 9, 35, 120])
+    want = ref.cressman_reference(cx, cy, sx, sy, obs, radii)
+    monkeypatch.setenv("IPR_CR_XDIV", xdiv)
+    got = engine.cressman_grid(cx, cy, sx, sy, obs, radii)
+    for i in range(len(radii)):
+        assert_parity(got[i], want[i], label=f"cressman xdiv={xdiv} R={radii[i]:.0f}")
+
+
+def test_cressman_weights_at_the_cut_off_are_the_references():
+    """A station exactly R away from a cell centre (d == R: weight 0/(2 R^2) = 0, still 'in range' for the
+    denominator test) and stations a rounding error inside / outside the radius: the fused kernel computes
+    dist = sqrt(dx^2 + dy^2), dist_sq = dist * dist and the cut-off dist > R like R/Cressman.R:279-300."""
+    cx, cy = synthetic.regular_grid(12, 9)
+    R = 5000.0
+    sx = np.array([cx[0] + R, cx[5] + 3000.0, cx[17] + R * (1 + 2e-16), cx[30] - R * (1 - 2e-16), cx[40] + 1.0])
+    sy = np.array([cy[0], cy[5] + 4000.0, cy[17], cy[30], cy[40] + 1.0])
+    rng = np.random.default_rng(4)
+    obs = np.round(rng.gamma(0.8, 8.0, (40, sx.size)), 1) + 0.1
+    got = engine.cressman_grid(cx, cy, sx, sy, obs, np.array([R]))
+    assert_parity(got[0], ref.cressman_reference(cx, cy, sx, sy, obs, np.array([R]))[0], label="cut-off")
+
+
 def test_cressman_radius_without_neighbours_is_all_na():
     cx, cy, sx, sy, obs = synthetic.synthetic_case(6, 6, 4, 5, seed=2)
     got = engine.cressman_grid(cx, cy, sx + 1e6, sy, obs, np.array([1000.0]))
