@@ -1798,6 +1798,13 @@ private:
     std::vector<int> cpus_;
 };
 
+// IPR_D2H_ROWS=1: a device's column range of the caller's pinned matrix is written layer by layer with 1-D copies
+// instead of one pitched 2-D copy per chunk (experiment: is the pitched D2H the slower one?)
+bool rowwise_d2h() {
+    static const bool v = getenv("IPR_D2H_ROWS") && atoi(getenv("IPR_D2H_ROWS")) != 0;
+    return v;
+}
+
 // One device's share of a host-buffer job: cells [c0, c1) for every date (and every stack).
 int run_device_block(const HostJob& job, int device, long long c0, long long c1, char* err, size_t errlen) {
     if (c0 >= c1) return IPR_OK;
@@ -1907,6 +1914,11 @@ int run_device_block(const HostJob& job, int device, long long c0, long long c1,
         if (job.out_pinned) {
             if (width == pitch)
                 IPR_CUDA(cudaMemcpyAsync(dst, g.ring[slot], width * rows, cudaMemcpyDeviceToHost, g.copy));
+            else if (rowwise_d2h())
+                for (size_t rr = 0; rr < rows; rr++)
+                    IPR_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(dst) + rr * pitch,
+                                             reinterpret_cast<const char*>(g.ring[slot]) + rr * width, width,
+                                             cudaMemcpyDeviceToHost, g.copy));
             else
                 IPR_CUDA(cudaMemcpy2DAsync(dst, pitch, g.ring[slot], width, width, rows, cudaMemcpyDeviceToHost, g.copy));
         } else if ((rc = sink.push2d(reinterpret_cast<const char*>(g.ring[slot]), reinterpret_cast<char*>(dst), width,

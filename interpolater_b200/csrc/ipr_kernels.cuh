@@ -568,9 +568,6 @@ constexpr int kCrListPad = 16;                         // list capacity granule 
 #ifndef IPR_CR_PROFILE
 #define IPR_CR_PROFILE 0   // 1: per-phase cycle counters in cressman_kernel (IPR_CR_PROF=1 prints them); costs registers
 #endif
-#ifndef IPR_CR_APREF
-#define IPR_CR_APREF 1     // A fragments fetched this many stages ahead of their use (registers)
-#endif
 #ifndef IPR_CR_STAGES2
 #define IPR_CR_STAGES2 12
 #endif
@@ -797,17 +794,9 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
             for (int lin = 0; lin < kStages && lin < total; lin++) produce(lin);
 
         double w_cur[kCrKSteps];
-#if IPR_CR_APREF == 2
-        double w_nx1[kCrKSteps];
-#endif
         if (ns > 0) {
 #pragma unroll
             for (int kk = 0; kk < kCrKSteps; kk++) w_cur[kk] = panel[(size_t)kk * kThreads];
-#if IPR_CR_APREF == 2
-            const int i1 = (ns > 1) ? 1 : 0;
-#pragma unroll
-            for (int kk = 0; kk < kCrKSteps; kk++) w_nx1[kk] = panel[(size_t)(i1 * kCrKSteps + kk) * kThreads];
-#endif
         }
         const double inv_wsum = 1.0 / wsum;
         if (IPR_CR_PROFILE && args.prof) { const long long t = clock64(); pf[0] += t - pt0; pt0 = t; }
@@ -826,13 +815,8 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
                 const double* zs = reinterpret_cast<const double*>(smem + slot * L::kStageBytes);
                 double w_next[kCrKSteps];
                 {
-#if IPR_CR_APREF == 2
-                    int in = i + 2;                              // wraps into the next date tile (same panel)
-                    if (in >= ns) in -= ns;
-                    if (in >= ns) in -= ns;
-#else
+                    // (two stages ahead was measured too: 88.9 against 87.2 ms per cfg-4 step)
                     const int in = (i + 1 < ns) ? i + 1 : 0;     // the first stage of the next date tile
-#endif
 #pragma unroll
                     for (int kk = 0; kk < kCrKSteps; kk++) w_next[kk] = panel[(size_t)(in * kCrKSteps + kk) * kThreads];
                 }
@@ -866,14 +850,7 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
                 if (IPR_CR_PROFILE && args.prof) { const long long t = clock64(); pf[3] += t - pt0; pt0 = t; }
                 if (lane == 0) mbar_arrive(&empty_bar[slot]);   // this warp's reads of the slot are done (release)
 #pragma unroll
-                for (int kk = 0; kk < kCrKSteps; kk++) {
-#if IPR_CR_APREF == 2
-                    w_cur[kk] = w_nx1[kk];
-                    w_nx1[kk] = w_next[kk];
-#else
-                    w_cur[kk] = w_next[kk];
-#endif
-                }
+                for (int kk = 0; kk < kCrKSteps; kk++) w_cur[kk] = w_next[kk];
                 if (IPR_CR_PROFILE && args.prof) { const long long t = clock64(); pf[4] += t - pt0; pt0 = t; }
             }
             // ---- epilogue of this date tile: normalise, NA rule (R/Cressman.R:316-317), store ----

@@ -8,7 +8,7 @@ set -u
 T=$(mktemp -d)
 O=gpurun_out/r02_asan.log
 nvcc -gencode arch=compute_100a,code=sm_100a -O1 -g -lineinfo -std=c++17 -shared -Xcompiler -fPIC \
-     -Xcompiler -fsanitize=address,undefined -Xcompiler -fno-omit-frame-pointer -I include \
+     -Xcompiler -fsanitize=address -Xcompiler -fsanitize=undefined -Xcompiler -fno-omit-frame-pointer -I include \
      -o $T/libinterpolater_b200.so interpolater_b200/csrc/ipr_api.cu > $O 2>&1 || { echo "asan build failed" >> $O; exit 1; }
 gcc -std=c11 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -Wno-cast-function-type \
     -I tests/mock_r -I include tests/mock_r/mock_runtime.c r-package/src/r_shim.c \

@@ -53,8 +53,10 @@ os.environ["IPR_TRACE"] = "1"
 cx, cy, sx, sy, obs = synthetic.synthetic_case(1000, 1000, 2000, D)
 obs_f = np.asfortranarray(obs)
 out = host.numpy().T          # (C, D) Fortran-ordered view of the pinned matrix
+# IPR_D2H_ROWS is read once per process: the row-wise variant is run by re-executing this script with the switch set
+mode = os.environ.get("IPR_D2H_ROWS", "0")
 for i in range(4):
     t = time.perf_counter()
     engine.idw_grid(cx, cy, sx, sy, obs_f, out=out, devices=list(range(n)))
-    print("ipr_idw_f64(devices=0..%d) call %d: %.1f ms" % (n - 1, i, (time.perf_counter() - t) * 1e3), flush=True)
+    print("ipr_idw_f64(devices=0..%d, IPR_D2H_ROWS=%s) call %d: %.1f ms" % (n - 1, mode, i, (time.perf_counter() - t) * 1e3), flush=True)
     print("---- call", i, file=sys.stderr, flush=True)
