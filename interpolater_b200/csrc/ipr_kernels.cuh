@@ -1142,7 +1142,13 @@ constexpr int kUStages = 8;
 constexpr int kUStageBytes = kUKbs * (kUABytes + kUBBytes);   // 22 528
 constexpr int kUThreads = 192;                             // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
 constexpr int kUTmemCols = 512;                            // two accumulator buffers of 224 columns (at 0 and 256)
-constexpr int kUSmemBytes = kUStages * kUStageBytes + (2 * kUStages + 4) * 8 + 16;
+constexpr int kUBarBytes = (2 * kUStages + 4) * 8 + 16;
+// epilogue staging: every epilogue warp transposes its 32 dates x 32 cells through shared memory (rows padded to 33
+// doubles) so that a store instruction writes 32 consecutive cells of ONE layer (256 contiguous bytes) instead of
+// 16 bytes in each of 32 layers
+constexpr int kUStageLd = kUCells + 1;
+constexpr int kUStagingOff = kUStages * kUStageBytes + ((kUBarBytes + 15) / 16) * 16;
+constexpr int kUSmemBytes = kUStagingOff + 4 * 32 * kUStageLd * 8;
 constexpr double kQDirectBelow = 0x1p-10;                  // denominators below this share of the scale are re-evaluated in FP64
 static_assert(kQKbPad % kUKbs == 0, "whole pipeline stages");
 
@@ -1351,7 +1357,7 @@ __global__ void __launch_bounds__(kUThreads, 1) denom_umma_kernel(const DenomArg
     } else {
         const int quarter = warp & 3;              // TMEM lanes [32 quarter, 32 quarter + 32) belong to this warp
         const int row = quarter * 32 + lane;       // date inside the granule
-        const bool vec_ok = ((args.ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(args.out) & 15) == 0);
+        double* stg = reinterpret_cast<double*>(usm + kUStagingOff) + quarter * 32 * kUStageLd;
         int tl = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tl++) {
             const int buf = tl & 1;
@@ -1361,7 +1367,6 @@ __global__ void __launch_bounds__(kUThreads, 1) denom_umma_kernel(const DenomArg
             const double scale_l = scalbn(1.0, row_exponent(args.wmax[cell0 + lane]));   // lane <-> cell of the group
             const bool t_ok = (t >= args.t_lo && t < args.t_hi);
             const bool listable = t_ok && args.date_flag[t] == 0;
-            double* orow = args.out + (long long)(t_ok ? t - args.t_lo : 0) * args.ld_out + cell0;
             mbar_wait(&tfull_bar[buf], (tl >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tbase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * 256u;
@@ -1398,18 +1403,22 @@ __global__ void __launch_bounds__(kUThreads, 1) denom_umma_kernel(const DenomArg
                     }
                     d[i] *= sc;
                 }
-                if (t_ok) {
-                    double* o = orow + c8 * 8;
-                    if (vec_ok && cell0 + c8 * 8 + 8 <= args.n_cells) {
 #pragma unroll
-                        for (int i = 0; i < 8; i += 2) *reinterpret_cast<double2*>(o + i) = make_double2(d[i], d[i + 1]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; i++)
-                            if (cell0 + c8 * 8 + i < args.n_cells) o[i] = d[i];
-                    }
+                for (int i = 0; i < 8; i++) stg[lane * kUStageLd + c8 * 8 + i] = d[i];
+            }
+            __syncwarp();
+            // transposed write-out: lane <-> cell, one layer per instruction
+            {
+                const int t_first = t - lane;                       // date of TMEM lane 0 of this warp
+                const bool cell_ok = cell0 + lane < args.n_cells;
+                double* o = args.out + (long long)(t_first - args.t_lo) * args.ld_out + cell0 + lane;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; rr++) {
+                    const int tr = t_first + rr;
+                    if (cell_ok && tr >= args.t_lo && tr < args.t_hi) o[(long long)rr * args.ld_out] = stg[rr * kUStageLd + lane];
                 }
             }
+            __syncwarp();   // the staging tile is rewritten by the next accumulator tile
         }
     }
     tc_fence_before();
