@@ -191,6 +191,25 @@ def test_many_stations_and_wide_station_extent():
         assert_parity(got[i], want[i], label=f"S=1100 cressman {i}")
 
 
+def test_cressman_long_station_lists():
+    """The branches of the fused Cressman kernel that the other cases never reach: a tile whose station list is
+    longer than its shared-memory copy (2,048 entries: the refilling warp reads the list from global memory),
+    more listed stations than one coordinate chunk of the panel generation (2,048), and more 8-station groups
+    than one candidate round holds (4,096 groups = 32,768 stations)."""
+    rng = np.random.default_rng(77)
+    cx, cy = synthetic.regular_grid(11, 7)
+    n_st = 33500                                   # 4,188 groups: two candidate rounds
+    sx = cx.min() + rng.random(n_st) * 40e3 - 15e3
+    sy = cy.min() + rng.random(n_st) * 40e3 - 15e3
+    obs = np.round(rng.gamma(0.8, 8.0, (6, n_st)), 1)
+    obs[rng.random(obs.shape) < 0.1] = np.nan
+    radii = np.array([1500.0, 60e3])               # ~100 stations in range / all 33,500 of them
+    got = engine.cressman_grid(cx, cy, sx, sy, obs, radii)
+    want = ref.cressman_reference(cx, cy, sx, sy, obs, radii)
+    for i in range(2):
+        assert_parity(got[i], want[i], label=f"S=33500 cressman R={radii[i]:.0f}")
+
+
 def test_duplicate_cells_and_all_stations_on_cells():
     """Every station sits on a cell centre and some cells are listed twice (the C ABI takes arbitrary
     cell arrays): zero-distance bookkeeping with many pairs."""
