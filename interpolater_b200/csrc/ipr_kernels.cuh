@@ -772,9 +772,7 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
         // stage starved the pipeline — ncu: 23 % of the warp samples spinning on the full barrier, DMMA pipe 70 %
         // active; the bulk-copy engine wants few large requests.)  Every lane's copies arrive on the slot's
         // barrier when they have landed.
-        auto produce = [&](int lin) {
-            const int jt = lin / ns, i = lin - jt * ns;
-            const int slot = (int)((it_base + (unsigned)lin) % kStages);
+        auto produce = [&](int jt, int i, int slot) {
 #pragma unroll
             for (int r0 = 0; r0 < kCrRows; r0 += 8) {
                 const int row = r0 + (lane >> 2);
@@ -791,7 +789,16 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[slot])) : "memory");
         };
         if (warp == 0)
-            for (int lin = 0; lin < kStages && lin < total; lin++) produce(lin);
+            for (int lin = 0; lin < kStages && lin < total; lin++)
+                produce(lin / ns, lin % ns, (int)((it_base + (unsigned)lin) % kStages));
+        // running pipeline state (no division or modulo in the stage loop): slot / parity of the current stage,
+        // the (date tile, stage) that the refill duty of the current stage would gather, and whose turn it is
+        int slot = (int)(it_base % kStages);
+        unsigned par = (it_base / kStages) & 1u;
+        int pj = (kStages - kLag) / max(ns, 1), pi = (kStages - kLag) % max(ns, 1);
+        // stages until this warp's next turn at the refill duty (a turn before stage kLag has nothing to refill)
+        int to_duty = (int)(((unsigned)kLag + (unsigned)warp - it_base) & (kConsumerWarps - 1));
+        if (to_duty < kLag) to_duty += kConsumerWarps;
 
         double w_cur[kCrKSteps];
         if (ns > 0) {
@@ -809,9 +816,6 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
                 acc[i][1] = 0.0;
             }
             for (int i = 0; i < ns; i++) {
-                const int i_lin = jt * ns + i;
-                const unsigned it = it_base + (unsigned)i_lin;
-                const int slot = (int)(it % kStages);
                 const double* zs = reinterpret_cast<const double*>(smem + slot * L::kStageBytes);
                 double w_next[kCrKSteps];
                 {
@@ -824,16 +828,23 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
                 // the slot of stage lin - kLag and gathers stage lin - kLag + kStages into it.  (The last warp to
                 // release used to refill: the slowest warp got the extra work every time, fell further behind, and
                 // the other SMSPs' DMMA pipes idled behind the 8-stage window — 14 % of the samples on this wait.)
-                if (((it - kLag) & (kConsumerWarps - 1)) == (unsigned)warp && i_lin >= kLag && i_lin - kLag + kStages < total) {
-                    const unsigned itr = it - kLag;
+                if (to_duty == 0 && pj < args.tiles.n) {
+                    // the slot released kLag stages ago: kLag = kStages / 2 slots away, on the other parity if that wraps
+                    const int slot_r = slot >= kLag ? slot - kLag : slot + (kStages - kLag);
+                    const unsigned par_r = slot >= kLag ? par : par ^ 1u;
                     long long ta = (IPR_CR_PROFILE && args.prof) ? clock64() : 0;
-                    mbar_wait(&empty_bar[itr % kStages], (itr / kStages) & 1);
+                    mbar_wait(&empty_bar[slot_r], par_r);
                     if (IPR_CR_PROFILE && args.prof) { const long long t = clock64(); pf[6] += t - ta; ta = t; }
-                    produce(i_lin - kLag + kStages);
+                    produce(pj, pi, slot_r);
                     if (IPR_CR_PROFILE && args.prof) { const long long t = clock64(); pf[7] += t - ta; }
                 }
+                to_duty = (to_duty == 0) ? kConsumerWarps - 1 : to_duty - 1;
+                if (++pi == ns) {
+                    pi = 0;
+                    pj++;
+                }
                 if (IPR_CR_PROFILE && args.prof) { const long long t = clock64(); pf[1] += t - pt0; pt0 = t; }
-                mbar_wait(&full_bar[slot], (it / kStages) & 1);
+                mbar_wait(&full_bar[slot], par);
                 if (IPR_CR_PROFILE && args.prof) { const long long t = clock64(); pf[2] += t - pt0; pt0 = t; }
 #pragma unroll
                 for (int kk = 0; kk < kCrKSteps; kk++) {
@@ -851,6 +862,10 @@ __global__ void __launch_bounds__(kThreads, 2) cressman_kernel(const CressmanArg
                 if (lane == 0) mbar_arrive(&empty_bar[slot]);   // this warp's reads of the slot are done (release)
 #pragma unroll
                 for (int kk = 0; kk < kCrKSteps; kk++) w_cur[kk] = w_next[kk];
+                if (++slot == kStages) {
+                    slot = 0;
+                    par ^= 1u;
+                }
                 if (IPR_CR_PROFILE && args.prof) { const long long t = clock64(); pf[4] += t - pt0; pt0 = t; }
             }
             // ---- epilogue of this date tile: normalise, NA rule (R/Cressman.R:316-317), store ----
