@@ -21,6 +21,10 @@
 #include <thread>
 #include <vector>
 
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define IPR_HAVE_SSE2 1
+#endif
 #include <pthread.h>
 #include <sched.h>
 #include <sys/mman.h>
@@ -1621,6 +1625,43 @@ struct AffinityScope {
 // fresh 29 GB matrix with cudaHostRegister instead was measured at 7.2 s (page faults taken one by
 // one inside the driver); first-touching it from many threads is what makes this path fast.
 // ---------------------------------------------------------------------------------------------
+// Staging slot -> the caller's pageable matrix with non-temporal stores.  An ordinary store to a line that is not
+// in cache first READS the line (read for ownership): with the GPU's DMA writing the next slot at PCIe rate at
+// the same time, that fourth stream of memory traffic is what held the pageable path at 720-820 ms per 29.2 GB
+// against 550 ms for a pinned result.  glibc's memcpy only switches to streaming stores above a threshold tied to
+// the shared cache size (hundreds of MB on these hosts), far above the 16 MiB a drain thread copies per slot.
+// IPR_NT_COPY=0 restores memcpy.
+inline bool nt_copy_enabled() {
+    static const bool v = !(getenv("IPR_NT_COPY") && atoi(getenv("IPR_NT_COPY")) == 0);
+    return v;
+}
+inline void copy_to_pageable(char* dst, const char* src, size_t n) {
+#ifdef IPR_HAVE_SSE2
+    if (nt_copy_enabled() && n >= 4096) {
+        size_t head = (64 - (reinterpret_cast<uintptr_t>(dst) & 63)) & 63;
+        memcpy(dst, src, head);
+        dst += head;
+        src += head;
+        n -= head;
+        const size_t lines = n / 64;
+        for (size_t i = 0; i < lines; i++) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 32));
+            const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 64 * i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i), a);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 64 * i + 48), d);
+        }
+        _mm_sfence();
+        memcpy(dst + lines * 64, src + lines * 64, n - lines * 64);
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
+
 class PageableSink {
 public:
     static constexpr size_t kSlotBytes = 256u << 20;
@@ -1764,7 +1805,7 @@ private:
                 const size_t per = (w.bytes / n_threads_ + 4095) & ~size_t(4095);
                 for (unsigned t = 0; t < n_threads_; t++) {
                     const size_t lo = std::min(w.bytes, (size_t)t * per), hi = std::min(w.bytes, lo + per);
-                    if (hi > lo) th.emplace_back([=] { memcpy(w.dst + lo, src + lo, hi - lo); });
+                    if (hi > lo) th.emplace_back([=] { copy_to_pageable(w.dst + lo, src + lo, hi - lo); });
                 }
             } else {
                 const size_t rows = w.bytes / w.width;
@@ -1773,7 +1814,7 @@ private:
                     const size_t lo = std::min(rows, (size_t)t * per), hi = std::min(rows, lo + per);
                     if (hi > lo)
                         th.emplace_back([=] {
-                            for (size_t r = lo; r < hi; r++) memcpy(w.dst + r * w.pitch, src + r * w.width, w.width);
+                            for (size_t r = lo; r < hi; r++) copy_to_pageable(w.dst + r * w.pitch, src + r * w.width, w.width);
                         });
                 }
             }
