@@ -73,7 +73,9 @@ def workload_name(a, wl):
     if wl == "idw":
         return f"synthetic IDW (cfg 3): {base}, p=2, no NA"
     if wl == "idw_masked":
-        return f"synthetic IDW (cfg 5): {base}, p=2, 20% per-date NA (masked contraction)"
+        return (f"synthetic IDW (cfg 5): {base}, p=2, 20% per-date NA (masked contraction); all {a.stations:,} stations "
+                "train here — the training=0.8 hold-out + validation of configs[4] runs at full size in "
+                "tests/test_gpu_parity.py::test_full_size_cfg5_through_the_drop_in_signature")
     return f"synthetic Cressman (cfg 4): {base}, 4 radii (25/50/100/200 km)"
 
 
