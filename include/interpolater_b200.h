@@ -93,6 +93,24 @@ int ipr_idw_kriging_f64(const double* cell_x, const double* cell_y, int64_t n_ce
                         const int* devices, int n_devices,
                         double* out, char* err, size_t errlen);
 
+/* Ordinary kriging, the prediction step of perform_kriging for every date (R/Kriging_Ordinary.R:405-508).
+ * The empirical variogram, its fit (optim) and the decision to fall back stay in R; per date t the caller passes
+ *   model[t]  0 = fall back to IDW (flat variogram, det == 0 or kappa > 1e12, :428-462)
+ *             1 exponential | 2 spherical | 3 gaussian | 4 linear        (variogram_models, :262-275)
+ *   nugget[t], sill[t], range[t]   the fitted parameters (ignored when model[t] == 0)
+ * Per date: the prelude of ipr_idw_kriging_f64 (constant layers), then for model > 0
+ *   Gamma = variogram matrix of the n stations available on the date (nugget on the diagonal, Lagrange row / column),
+ *   alpha = Gamma^-1 [v; 0]                       ONE (n+1)^2 LU per date — the reference solves per cell
+ *   out[c, t] = max(0, alpha_n + sum_i alpha_i gamma_t(d(c, s_i)))       = max(0, sum(w * v)) with Gamma w = [gamma(c); 1]
+ * and mean(v) where Gamma is exactly singular (the reference's tryCatch, :494).  The two orders of solving agree to
+ * kappa(Gamma) * 2^-53. */
+int ipr_kriging_f64(const double* cell_x, const double* cell_y, int64_t n_cells,
+                    const double* st_x, const double* st_y, int32_t n_st,
+                    const double* obs, int32_t n_dates,
+                    const int32_t* model, const double* nugget, const double* sill, const double* range,
+                    const int* devices, int n_devices,
+                    double* out, char* err, size_t errlen);
+
 /* ---------------------------------------------------------------------------------------
  * The same two calls with the reference's next steps fused on the device, so that a large stack
  * needs no further host pass:
@@ -184,6 +202,9 @@ int ipr_plan_idw(ipr_plan* plan, double p, int32_t t0, int32_t t1,
 /* the Kriging fallback rule of ipr_idw_kriging_f64 */
 int ipr_plan_idw_kriging(ipr_plan* plan, int32_t t0, int32_t t1,
                          double* d_out, int64_t ld_out, char* err, size_t errlen);
+/* ordinary kriging (ipr_kriging_f64); model / nugget / sill / range are HOST arrays of n_dates entries */
+int ipr_plan_kriging(ipr_plan* plan, const int32_t* model, const double* nugget, const double* sill, const double* range,
+                     int32_t t0, int32_t t1, double* d_out, int64_t ld_out, char* err, size_t errlen);
 /* radius ri's stack starts at d_out + ri * stack_stride (elements) */
 int ipr_plan_cressman(ipr_plan* plan, const double* radii_m, int32_t n_radii,
                       int32_t t0, int32_t t1, double* d_out, int64_t ld_out,

@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "ipr_plan_stream", "ipr_host_alloc", "ipr_host_free", "ipr_release_cached_memory",
     "ipr_job_start_idw", "ipr_job_start_cressman", "ipr_job_wait", "ipr_job_cancel", "ipr_job_finish",
     "ipr_cell_split_bounds", "ipr_idw_kriging_f64", "ipr_plan_idw_kriging",
+    "ipr_kriging_f64", "ipr_plan_kriging",
 ]
 
 
@@ -71,6 +72,11 @@ def load() -> C.CDLL:
                                         ip, C.c_int, vp, C.c_char_p, C.c_size_t]
     lib.ipr_plan_idw_kriging.restype = C.c_int
     lib.ipr_plan_idw_kriging.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int64, C.c_char_p, C.c_size_t]
+    lib.ipr_kriging_f64.restype = C.c_int
+    lib.ipr_kriging_f64.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, vp, vp, vp, vp,
+                                    ip, C.c_int, vp, C.c_char_p, C.c_size_t]
+    lib.ipr_plan_kriging.restype = C.c_int
+    lib.ipr_plan_kriging.argtypes = [vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int64, C.c_char_p, C.c_size_t]
     lib.ipr_cressman_f64.restype = C.c_int
     lib.ipr_cressman_f64.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, vp, C.c_int32,
                                      ip, C.c_int, vp, C.c_char_p, C.c_size_t]

@@ -1349,6 +1349,124 @@ int ipr_plan_idw_kriging(ipr_plan* p, int32_t t0, int32_t t1, double* d_out, int
     return no_throw(err, errlen, [&] { return plan_idw_kriging_impl(p, t0, t1, d_out, ld_out, err, errlen); });
 }
 
+// Ordinary kriging over [t0, t1) (R/Kriging_Ordinary.R:405-508).  model[t] (host arrays indexed by absolute date):
+// 0 = the date falls back to IDW (flat variogram, singular or ill-conditioned Gamma: decided in R, :428-462),
+// 1..4 = exponential / spherical / gaussian / linear with nugget[t], sill[t], range[t].  The fallback pass writes
+// every date of the range (IDW fallback + the constant layers of the prelude); the kriged dates are then
+// overwritten: one (n+1)^2 solve per date, then the cell x station variogram pass.
+static int plan_kriging_impl(ipr_plan* p, const int32_t* model, const double* nugget, const double* sill,
+                             const double* range, int32_t t0, int32_t t1, double* d_out, int64_t ld_out, char* err,
+                             size_t errlen) {
+    if (!model || !nugget || !sill || !range) {
+        set_err(err, errlen, "NULL argument");
+        return IPR_EINVAL;
+    }
+    int rc = check_range(p, t0, t1, d_out, ld_out, err, errlen);
+    if (rc) return rc;
+    if (t0 == t1) return IPR_OK;
+    // the post pass (rounding / mask) must run once, after the kriged dates are in place
+    const int post_mode = p->post_round_mode;
+    uint8_t* const post_keep = p->d_cell_keep;
+    p->post_round_mode = 0;
+    p->d_cell_keep = nullptr;
+    rc = plan_idw_kriging_impl(p, t0, t1, d_out, ld_out, err, errlen);
+    p->post_round_mode = post_mode;
+    p->d_cell_keep = post_keep;
+    if (rc) return rc;
+    std::vector<int> list;
+    for (int t = t0; t < t1; t++) {
+        if (model[t] == 0) continue;
+        if (model[t] < 1 || model[t] > 4 || !(range[t] > 0.0) || !std::isfinite(nugget[t]) || !std::isfinite(sill[t]) ||
+            !std::isfinite(range[t])) {
+            set_err(err, errlen, "date %d: variogram model must be 0..4 with finite nugget / sill and range > 0", t);
+            return IPR_EINVAL;
+        }
+        list.push_back(t);
+    }
+    if (!list.empty()) {
+        const int n1 = p->n_st + 1;
+        int n_sm = 0;
+        IPR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
+        const size_t per_cta = sizeof(double) * (size_t)n1 * (n1 + 1);
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>({list.size(), (size_t)n_sm, (size_t)(8ull << 30) / per_cta}));
+        const size_t n_list = list.size();
+        double *d_scratch = nullptr, *d_alpha = nullptr, *d_par = nullptr, *d_fb = nullptr;
+        int *d_list = nullptr, *d_avail = nullptr, *d_meta = nullptr, *d_model = nullptr;
+        struct Free {
+            std::vector<void*> v;
+            ~Free() { for (void* q : v) dev_free(q); }
+        } fr;
+        auto grab = [&](auto** ptr, size_t bytes) -> cudaError_t {
+            const cudaError_t e = dev_malloc(ptr, bytes);
+            if (e == cudaSuccess) fr.v.push_back(*ptr);
+            return e;
+        };
+        IPR_CUDA(grab(&d_scratch, per_cta * grid));
+        IPR_CUDA(grab(&d_alpha, sizeof(double) * n_list * n1));
+        IPR_CUDA(grab(&d_avail, sizeof(int) * n_list * p->n_st));
+        IPR_CUDA(grab(&d_meta, sizeof(int) * n_list * 4));
+        IPR_CUDA(grab(&d_fb, sizeof(double) * n_list));
+        IPR_CUDA(grab(&d_list, sizeof(int) * n_list));
+        IPR_CUDA(grab(&d_par, sizeof(double) * 3 * p->n_dates));
+        IPR_CUDA(grab(&d_model, sizeof(int) * p->n_dates));
+        IPR_CUDA(cudaMemcpyAsync(d_list, list.data(), sizeof(int) * n_list, cudaMemcpyHostToDevice, p->stream));
+        IPR_CUDA(cudaMemcpyAsync(d_par, nugget, sizeof(double) * p->n_dates, cudaMemcpyHostToDevice, p->stream));
+        IPR_CUDA(cudaMemcpyAsync(d_par + p->n_dates, sill, sizeof(double) * p->n_dates, cudaMemcpyHostToDevice, p->stream));
+        IPR_CUDA(cudaMemcpyAsync(d_par + 2 * (size_t)p->n_dates, range, sizeof(double) * p->n_dates, cudaMemcpyHostToDevice,
+                                 p->stream));
+        IPR_CUDA(cudaMemcpyAsync(d_model, model, sizeof(int) * p->n_dates, cudaMemcpyHostToDevice, p->stream));
+        IPR_CUDA(cudaMemsetAsync(d_meta, 0, sizeof(int) * n_list * 4, p->stream));
+        KrigingArgs k{};
+        k.dates = d_list;
+        k.n_list = (int)n_list;
+        k.nugget = d_par;
+        k.sill = d_par + p->n_dates;
+        k.range = d_par + 2 * (size_t)p->n_dates;
+        k.model = d_model;
+        k.kflag = p->d_kflag;
+        k.obs = p->d_obs;
+        k.ld_obs = p->n_dates;
+        k.perm = p->d_perm;
+        k.st_xy = p->d_st;
+        k.n_st = p->n_st;
+        k.scratch = d_scratch;
+        k.alpha = d_alpha;
+        k.avail = d_avail;
+        k.meta = d_meta;
+        k.fallback_value = d_fb;
+        {
+            PhaseScope ps(p, IPR_PHASE_FIXUP);
+            kriging_solve_kernel<<<grid, kKrigThreads, 0, p->stream>>>(k);
+            IPR_CUDA(cudaGetLastError());
+            p->launches++;
+        }
+        {
+            PhaseScope ps(p, IPR_PHASE_CONTRACT);
+            for (size_t l0 = 0; l0 < n_list; l0 += 32768) {   // gridDim.y <= 65535
+                KrigingArgs kk = k;
+                kk.dates = d_list + l0;
+                kk.alpha = d_alpha + l0 * n1;
+                kk.avail = d_avail + l0 * p->n_st;
+                kk.meta = d_meta + l0 * 4;
+                kk.fallback_value = d_fb + l0;
+                dim3 g((unsigned)((p->n_cells + 255) / 256), (unsigned)std::min<size_t>(32768, n_list - l0));
+                kriging_predict_kernel<<<g, 256, 0, p->stream>>>(kk, p->d_cell, p->n_cells, t0, d_out, ld_out);
+                IPR_CUDA(cudaGetLastError());
+                p->launches++;
+            }
+        }
+        // the scratch goes back to the pool below; the host arrays were copied from pageable memory
+        IPR_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    return run_post(p, t0, t1, d_out, ld_out, err, errlen);
+}
+
+int ipr_plan_kriging(ipr_plan* p, const int32_t* model, const double* nugget, const double* sill, const double* range,
+                     int32_t t0, int32_t t1, double* d_out, int64_t ld_out, char* err, size_t errlen) {
+    return no_throw(err, errlen,
+                    [&] { return plan_kriging_impl(p, model, nugget, sill, range, t0, t1, d_out, ld_out, err, errlen); });
+}
+
 int ipr_plan_set_post(ipr_plan* p, int32_t round_mode, int32_t n_round, const uint8_t* cell_keep, char* err,
                       size_t errlen) {
     if (!p) {
@@ -1500,6 +1618,8 @@ struct HostJob {
     int round_mode = 0, n_round = 0;
     const uint8_t* cell_keep = nullptr;
     bool kriging = false;                         // IDW fallback of Kriging_Ordinary instead of IDW()
+    const int32_t* kr_model = nullptr;            // with kriging: per-date variogram (ipr_kriging_f64), else fallback only
+    const double *kr_nugget = nullptr, *kr_sill = nullptr, *kr_range = nullptr;
     int n_job_devices = 1;                        // devices sharing the host's cores / memory bandwidth in this job
     // asynchronous jobs (ipr_job_*): cooperative cancellation and progress in work items (date chunks)
     std::atomic<int>* cancel = nullptr;
@@ -1944,7 +2064,9 @@ int run_device_block(const HostJob& job, int device, long long c0, long long c1,
         if (job.cressman)
             rc = ipr_plan_cressman(plan, job.radii + it.stack, 1, it.t0, it.t1, g.ring[slot], nc, 0, err, errlen);
         else
-            rc = job.kriging ? ipr_plan_idw_kriging(plan, it.t0, it.t1, g.ring[slot], nc, err, errlen)
+            rc = job.kriging ? (job.kr_model ? ipr_plan_kriging(plan, job.kr_model, job.kr_nugget, job.kr_sill, job.kr_range,
+                                                                it.t0, it.t1, g.ring[slot], nc, err, errlen)
+                                             : ipr_plan_idw_kriging(plan, it.t0, it.t1, g.ring[slot], nc, err, errlen))
                              : ipr_plan_idw(plan, job.p, it.t0, it.t1, g.ring[slot], nc, err, errlen);
         if (rc) return rc;
         IPR_CUDA(cudaEventRecord(g.computed[slot], plan->stream));
@@ -2194,6 +2316,23 @@ int ipr_idw_kriging_f64(const double* cell_x, const double* cell_y, int64_t n_ce
                         int n_devices, double* out, char* err, size_t errlen) {
     HostJob job{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, false, 2.0, nullptr, 0, out};
     job.kriging = true;
+    return no_throw(err, errlen, [&] { return run_host_job(job, devices, n_devices, err, errlen); });
+}
+
+int ipr_kriging_f64(const double* cell_x, const double* cell_y, int64_t n_cells, const double* st_x, const double* st_y,
+                    int32_t n_st, const double* obs, int32_t n_dates, const int32_t* model, const double* nugget,
+                    const double* sill, const double* range, const int* devices, int n_devices, double* out, char* err,
+                    size_t errlen) {
+    if (!model || !nugget || !sill || !range) {
+        set_err(err, errlen, "NULL argument");
+        return IPR_EINVAL;
+    }
+    HostJob job{cell_x, cell_y, st_x, st_y, obs, n_cells, n_st, n_dates, false, 2.0, nullptr, 0, out};
+    job.kriging = true;
+    job.kr_model = model;
+    job.kr_nugget = nugget;
+    job.kr_sill = sill;
+    job.kr_range = range;
     return no_throw(err, errlen, [&] { return run_host_job(job, devices, n_devices, err, errlen); });
 }
 

@@ -1526,4 +1526,262 @@ __global__ void post_kernel(double* __restrict__ out, long long ld_out, long lon
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ordinary kriging: the kriging branch of perform_kriging, R/Kriging_Ordinary.R:428-497.
+//
+// The reference solves Gamma w = [gamma(d(c, .)); 1] for EVERY cell (solve() inside apply, :489) and predicts
+// max(0, sum(w[1:n] * v)).  Gamma (the variogram matrix of the n stations available on the date, with the Lagrange
+// row and column) does not depend on the cell and is symmetric, so
+//     sum(w[1:n] v) = [v; 0]' Gamma^-1 [gamma(c); 1] = alpha' [gamma(c); 1],   alpha = Gamma^-1 [v; 0]:
+// ONE (n+1)^2 factorisation and solve per date (kriging_solve_kernel, one CTA per date, LU with partial pivoting
+// on [Gamma | v] in an L2-resident scratch), then a cell x station pass that evaluates the date's variogram model
+// on the fly (kriging_predict_kernel).  The variogram parameters are fitted per date in R and differ from date to
+// date, so there is no shared A operand and no GEMM here: both kernels run on the FP64 vector pipe.
+// ---------------------------------------------------------------------------------------------
+enum VariogramModel : int { kVarioExponential = 1, kVarioSpherical = 2, kVarioGaussian = 3, kVarioLinear = 4 };
+
+// variogram_models(), R/Kriging_Ordinary.R:262-275
+__device__ __forceinline__ double variogram_value(double h, double nugget, double sill, double range, int model) {
+    switch (model) {
+        case kVarioExponential: return nugget + sill * (1.0 - exp(-3.0 * h / range));
+        case kVarioSpherical: {
+            const double u = h / range;
+            return h <= range ? nugget + sill * (1.5 * h / range - 0.5 * (u * u * u)) : nugget + sill;
+        }
+        case kVarioGaussian: {
+            const double u = h / range;
+            return nugget + sill * (1.0 - exp(-3.0 * (u * u)));
+        }
+        default: return h <= range ? nugget + sill * h / range : nugget + sill;
+    }
+}
+
+struct KrigingArgs {
+    const int* dates;            // [n_list] absolute dates to krige
+    int n_list;
+    const double* nugget;        // [n_dates], indexed by absolute date
+    const double* sill;
+    const double* range;
+    const int* model;
+    const uint8_t* kflag;        // [n_dates] 3: constant layer (prelude), never kriged
+    const double* obs;           // column-major n_dates x n_st, input station order
+    long long ld_obs;
+    const int* perm;             // sorted position -> input station
+    const double2* st_xy;        // stations in sorted order
+    int n_st;
+    double* scratch;             // per CTA: (n_st + 1) x (n_st + 2) doubles, column-major, ld = n_st + 1
+    double* alpha;               // per list entry: n_st + 1 doubles (solution, packed over the available stations)
+    int* avail;                  // per list entry: n_st ints (sorted positions of the available stations)
+    int* meta;                   // per list entry: [0] n available, [1] status (0 solved, 1 skipped, 2 singular), [2..3] unused
+    double* fallback_value;      // per list entry: mean of the available values (solve() failed, :494)
+};
+
+constexpr int kKrigThreads = 512;
+
+__global__ void __launch_bounds__(kKrigThreads) kriging_solve_kernel(const KrigingArgs a) {
+    __shared__ int s_n;
+    __shared__ int s_warp_cnt[kKrigThreads / 32];
+    __shared__ double s_red_v[kKrigThreads / 32];
+    __shared__ int s_red_i[kKrigThreads / 32];
+    __shared__ int s_piv;
+    __shared__ double s_pivval;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ld = a.n_st + 1;
+    double* G = a.scratch + (size_t)blockIdx.x * ld * (ld + 1);
+    for (int li = blockIdx.x; li < a.n_list; li += gridDim.x) {
+        const int t = a.dates[li];
+        int* avail = a.avail + (size_t)li * a.n_st;
+        int* meta = a.meta + (size_t)li * 4;
+        double* alpha = a.alpha + (size_t)li * ld;
+        if (a.kflag[t] == 3) {                       // constant layer of the prelude: nothing to solve
+            if (tid == 0) meta[1] = 1;
+            continue;
+        }
+        // ---- available stations, ascending sorted position (ordered block compaction) ----
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        for (int base = 0; base < a.n_st; base += kKrigThreads) {
+            const int s = base + tid;
+            bool ok = false;
+            if (s < a.n_st) {
+                const double v = a.obs[(long long)a.perm[s] * a.ld_obs + t];
+                ok = (v == v);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) s_warp_cnt[warp] = __popc(m);
+            __syncthreads();
+            int before = s_n, tot = 0;
+            for (int w = 0; w < kKrigThreads / 32; w++) {
+                if (w < warp) before += s_warp_cnt[w];
+                tot += s_warp_cnt[w];
+            }
+            if (ok) avail[before + __popc(m & ((1u << lane) - 1u))] = s;
+            __syncthreads();
+            if (tid == 0) s_n += tot;
+            __syncthreads();
+        }
+        const int n = s_n;
+        const int m1 = n + 1;                        // order of the system
+        const double nug = a.nugget[t], sil = a.sill[t], rng = a.range[t];
+        const int model = a.model[t];
+        __syncthreads();
+        // ---- [Gamma | b]: gamma(h_ij) off the diagonal, the nugget on it (matrix(nugget, n+1, n+1), :431-435),
+        //      ones in the last row / column, 0 in the corner; b = [v; 0] ----
+        for (long long e = tid; e < (long long)m1 * (m1 + 1); e += kKrigThreads) {
+            const int i = (int)(e % m1), j = (int)(e / m1);
+            double g;
+            if (j == m1) {
+                g = (i < n) ? a.obs[(long long)a.perm[avail[i]] * a.ld_obs + t] : 0.0;
+            } else if (i == n || j == n) {
+                g = (i == n && j == n) ? 0.0 : 1.0;
+            } else if (i == j) {
+                g = nug;
+            } else {
+                const double2 p = a.st_xy[avail[i]], q = a.st_xy[avail[j]];
+                const double dx = p.x - q.x, dy = p.y - q.y;
+                g = variogram_value(sqrt(dx * dx + dy * dy), nug, sil, rng, model);
+            }
+            G[(size_t)j * ld + i] = g;
+        }
+        __syncthreads();
+        // ---- Gaussian elimination with partial pivoting on the augmented matrix ----
+        bool singular = false;
+        for (int k = 0; k < m1; k++) {
+            double best = -1.0;
+            int bi = k;
+            for (int i = k + tid; i < m1; i += kKrigThreads) {
+                const double v = fabs(G[(size_t)k * ld + i]);
+                if (v > best) {
+                    best = v;
+                    bi = i;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) {
+                    best = ov;
+                    bi = oi;
+                }
+            }
+            if (lane == 0) {
+                s_red_v[warp] = best;
+                s_red_i[warp] = bi;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double bv = s_red_v[0];
+                int bb = s_red_i[0];
+                for (int w = 1; w < kKrigThreads / 32; w++)
+                    if (s_red_v[w] > bv || (s_red_v[w] == bv && s_red_i[w] < bb)) {
+                        bv = s_red_v[w];
+                        bb = s_red_i[w];
+                    }
+                s_piv = bb;
+                s_pivval = bv;
+            }
+            __syncthreads();
+            if (!(s_pivval > 0.0)) {                 // exactly singular: solve() raises, the reference takes the mean
+                singular = true;
+                break;
+            }
+            const int pr = s_piv;
+            if (pr != k)
+                for (int j = k + tid; j <= m1; j += kKrigThreads) {
+                    const double x = G[(size_t)j * ld + k];
+                    G[(size_t)j * ld + k] = G[(size_t)j * ld + pr];
+                    G[(size_t)j * ld + pr] = x;
+                }
+            __syncthreads();
+            // multipliers by true division, as LAPACK's dgetf2 scales a column whose pivot is not tiny: x / x is
+            // exactly 1, x * (1 / x) need not be — two coincident stations must leave an exactly zero row behind,
+            // which is how the reference's solve() detects the singular system
+            const double piv = G[(size_t)k * ld + k];
+            for (int i = k + 1 + tid; i < m1; i += kKrigThreads) G[(size_t)k * ld + i] /= piv;
+            __syncthreads();
+            // trailing update, columns k+1 .. m1 (the last one is b): coalesced down the rows
+            const int rows = m1 - k - 1;
+            if (rows > 0) {
+                const long long work = (long long)rows * (m1 - k);
+                for (long long e = tid; e < work; e += kKrigThreads) {
+                    const int i = k + 1 + (int)(e % rows), j = k + 1 + (int)(e / rows);
+                    G[(size_t)j * ld + i] = fma(-G[(size_t)k * ld + i], G[(size_t)j * ld + k], G[(size_t)j * ld + i]);
+                }
+            }
+            __syncthreads();
+        }
+        if (singular) {
+            // mean(available_values), :494 — sequential sum in station order like R's mean()
+            if (tid == 0) {
+                double sum = 0.0;
+                for (int i = 0; i < n; i++) sum += a.obs[(long long)a.perm[avail[i]] * a.ld_obs + t];
+                a.fallback_value[li] = sum / (double)n;
+                meta[0] = n;
+                meta[1] = 2;
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- back substitution (column-oriented: no reductions) ----
+        double* b = G + (size_t)m1 * ld;
+        for (int k = m1 - 1; k >= 0; k--) {
+            if (tid == 0) b[k] /= G[(size_t)k * ld + k];
+            __syncthreads();
+            const double xk = b[k];
+            for (int i = tid; i < k; i += kKrigThreads) b[i] = fma(-G[(size_t)k * ld + i], xk, b[i]);
+            __syncthreads();
+        }
+        for (int i = tid; i < m1; i += kKrigThreads) alpha[i] = b[i];
+        if (tid == 0) {
+            meta[0] = n;
+            meta[1] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+// out[c, t] = max(0, alpha_n + sum_i alpha_i * gamma_t(d(c, s_i)))   (:478-491); a date whose system was singular
+// gets mean(available_values) (:494); constant-layer dates are left as the fallback pass wrote them.
+__global__ void __launch_bounds__(256) kriging_predict_kernel(const KrigingArgs a, const double2* __restrict__ cell_xy,
+                                                               long long n_cells, int t_lo, double* __restrict__ out,
+                                                               long long ld_out) {
+    constexpr int kTile = 256;
+    __shared__ double2 s_xy[kTile];
+    __shared__ double s_al[kTile];
+    const int li = blockIdx.y;
+    const int t = a.dates[li];
+    const int* meta = a.meta + (size_t)li * 4;
+    const int status = meta[1];
+    if (status == 1) return;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double* optr = out + (long long)(t - t_lo) * ld_out + c;
+    if (status == 2) {
+        if (c < n_cells) *optr = a.fallback_value[li];
+        return;
+    }
+    const int n = meta[0];
+    const int ld = a.n_st + 1;
+    const double* alpha = a.alpha + (size_t)li * ld;
+    const int* avail = a.avail + (size_t)li * a.n_st;
+    const double nug = a.nugget[t], sil = a.sill[t], rng = a.range[t];
+    const int model = a.model[t];
+    const double2 cxy = (c < n_cells) ? cell_xy[c] : make_double2(0.0, 0.0);
+    double acc = 0.0;
+    for (int s0 = 0; s0 < n; s0 += kTile) {
+        const int m = min(kTile, n - s0);
+        __syncthreads();
+        if ((int)threadIdx.x < m) {
+            s_xy[threadIdx.x] = a.st_xy[avail[s0 + threadIdx.x]];
+            s_al[threadIdx.x] = alpha[s0 + threadIdx.x];
+        }
+        __syncthreads();
+        for (int i = 0; i < m; i++) {
+            const double dx = cxy.x - s_xy[i].x, dy = cxy.y - s_xy[i].y;
+            acc = fma(s_al[i], variogram_value(sqrt(dx * dx + dy * dy), nug, sil, rng, model), acc);
+        }
+    }
+    if (c < n_cells) *optr = fmax(0.0, acc + alpha[n]);
+}
+
 }  // namespace ipr

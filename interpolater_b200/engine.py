@@ -103,6 +103,40 @@ def idw_kriging_fallback_grid(cell_x, cell_y, st_x, st_y, obs, devices=None, out
     return out
 
 
+#: variogram model codes of ipr_kriging_f64 (0 = the date falls back to IDW)
+VARIOGRAM_MODELS = {"idw": 0, "exponential": 1, "spherical": 2, "gaussian": 3, "linear": 4}
+
+
+def kriging_grid(cell_x, cell_y, st_x, st_y, obs, model, nugget, sill, range_, devices=None, out=None):
+    """Ordinary kriging prediction for every cell x date (the prediction step of perform_kriging,
+    R/Kriging_Ordinary.R:405-508).  model / nugget / sill / range_: one entry per date — the variogram the caller
+    fitted for it (model by name or code; "idw" / 0 = the date falls back to IDW).  Returns (n_cells, n_dates)
+    float64, Fortran order; never NA."""
+    lib = _native.load()
+    cx, cy = _f64(cell_x, "cell_x"), _f64(cell_y, "cell_y")
+    sx, sy = _f64(st_x, "st_x"), _f64(st_y, "st_y")
+    if cx.shape != cy.shape or sx.shape != sy.shape:
+        raise ValueError("coordinate arrays must have matching lengths")
+    ob = _obs_colmajor(obs, sx.shape[0])
+    n_dates = ob.shape[0]
+    md = np.ascontiguousarray([VARIOGRAM_MODELS[m] if isinstance(m, str) else int(m) for m in np.atleast_1d(model)],
+                              dtype=np.int32)
+    par = [np.ascontiguousarray(np.atleast_1d(v), dtype=np.float64) for v in (nugget, sill, range_)]
+    if md.shape != (n_dates,) or any(v.shape != (n_dates,) for v in par):
+        raise ValueError("model, nugget, sill and range_ need one entry per date")
+    if out is None:
+        out = np.empty((cx.shape[0], n_dates), dtype=np.float64, order="F")
+    elif out.shape != (cx.shape[0], n_dates) or not out.flags.f_contiguous or out.dtype != np.float64:
+        raise ValueError("out must be a Fortran-ordered float64 (n_cells, n_dates) array")
+    dev, ndev = _devices(devices)
+    err = _native.errbuf()
+    rc = lib.ipr_kriging_f64(cx.ctypes.data, cy.ctypes.data, cx.shape[0], sx.ctypes.data, sy.ctypes.data, sx.shape[0],
+                             ob.ctypes.data, n_dates, md.ctypes.data, par[0].ctypes.data, par[1].ctypes.data,
+                             par[2].ctypes.data, dev, ndev, out.ctypes.data, err, _native.ERRLEN)
+    _native.check(rc, err)
+    return out
+
+
 def cressman_grid(cell_x, cell_y, st_x, st_y, obs, radii_m, devices=None, out=None, n_round=None,
                   round_mode=ROUND_TERRA, cell_keep=None):
     """Cressman analysis for each radius (metres, ascending unique).  Returns

@@ -176,6 +176,74 @@ def kriging_idw_fallback_one_date(dist_pred_obs, obs_vec):
     return (w * vals[None, :]).sum(axis=1) / w.sum(axis=1)       # :472
 
 
+VARIOGRAM_MODELS = {"exponential": 1, "spherical": 2, "gaussian": 3, "linear": 4}
+
+
+def variogram_models(h, nugget, sill, rng, model):
+    """variogram_models(), R/Kriging_Ordinary.R:262-275 (model by name or by the engine's code 1..4)."""
+    if not isinstance(model, str):
+        model = {v: k for k, v in VARIOGRAM_MODELS.items()}[int(model)]
+    h = np.asarray(h, dtype=np.float64)
+    if model == "exponential":
+        return nugget + sill * (1 - np.exp(-3 * h / rng))
+    if model == "spherical":
+        return np.where(h <= rng, nugget + sill * (1.5 * h / rng - 0.5 * (h / rng) ** 3), nugget + sill)
+    if model == "gaussian":
+        return nugget + sill * (1 - np.exp(-3 * (h / rng) ** 2))
+    if model == "linear":
+        return np.where(h <= rng, nugget + sill * h / rng, nugget + sill)
+    raise ValueError(model)
+
+
+def kriging_one_date(dist_pred_obs, dist_obs_obs, obs_vec, params):
+    """perform_kriging for one date, R/Kriging_Ordinary.R:405-508.  params: None or a dict with use_idw=True ->
+    the IDW fallback; else dict(nugget, sill, range, model).  The kriging branch is the literal per-cell
+    `solve(gamma_matrix, gamma_vector)` (:478-497): gamma_matrix is initialised with the nugget (so the diagonal
+    holds it), off-diagonal entries are the variogram of the station distances, the last row / column are 1 and
+    the corner 0 (:431-452); prediction max(0, sum(weights[1:n] * values)), mean(values) where solve() fails."""
+    obs_vec = np.asarray(obs_vec, dtype=np.float64)
+    if params is None or params.get("use_idw"):
+        return kriging_idw_fallback_one_date(dist_pred_obs, obs_vec)
+    avail = ~_is_na(obs_vec)
+    vals = obs_vec[avail]
+    n_cells = dist_pred_obs.shape[0]
+    if vals.size < 2:
+        return np.full(n_cells, float(vals.mean()) if vals.size > 0 else 0.0)
+    if np.unique(vals).size == 1:
+        return np.full(n_cells, float(vals[0]))
+    n = vals.size
+    nug, sill, rng, model = params["nugget"], params["sill"], params["range"], params["model"]
+    gm = np.full((n + 1, n + 1), float(nug))
+    h = dist_obs_obs[np.ix_(avail, avail)]
+    off = ~np.eye(n, dtype=bool)
+    gm[:n, :n][off] = variogram_models(h, nug, sill, rng, model)[off]
+    gm[n, :n] = 1.0
+    gm[:n, n] = 1.0
+    gm[n, n] = 0.0
+    out = np.empty(n_cells)
+    d = dist_pred_obs[:, avail]
+    for c in range(n_cells):
+        gv = np.append(variogram_models(d[c], nug, sill, rng, model), 1.0)
+        try:
+            w = np.linalg.solve(gm, gv)                       # LAPACK dgesv, like R's solve()
+            out[c] = max(0.0, float(np.sum(w[:n] * vals)))
+        except np.linalg.LinAlgError:
+            out[c] = float(vals.mean())
+    return out
+
+
+def kriging_reference(cx, cy, sx, sy, obs, params):
+    """All dates; params[t] as for kriging_one_date.  Returns (n_cells, n_dates), plus the worst 2-norm condition
+    number of the kriged dates' gamma matrices (the two solve orders agree to about kappa * 2^-53)."""
+    dist = distance_matrix(cx, cy, sx, sy)
+    dss = distance_matrix(sx, sy, sx, sy)
+    obs = np.asarray(obs, dtype=np.float64)
+    out = np.empty((dist.shape[0], obs.shape[0]), dtype=np.float64, order="F")
+    for t in range(obs.shape[0]):
+        out[:, t] = kriging_one_date(dist, dss, obs[t], params[t])
+    return out
+
+
 def kriging_idw_fallback_reference(cx, cy, sx, sy, obs):
     """All dates of `obs` (n_dates x n_stations) through kriging_idw_fallback_one_date; (n_cells, n_dates)."""
     dist = distance_matrix(cx, cy, sx, sy)

@@ -897,3 +897,89 @@ def test_kriging_idw_fallback_multi_shard_and_after_idw():
     many = engine.idw_kriging_fallback_grid(cx, cy, sx, sy, obs, devices=[0, 0, 0])
     assert_parity(many, one, tol=1e-12, label="kriging fallback shards")
     assert_parity(one, ref.kriging_idw_fallback_reference(cx, cy, sx, sy, obs), label="kriging fallback")
+
+
+# ---------------------------------------------------------------- ordinary kriging (the kriging branch)
+def _kriging_params(n_dates, rng, models=("exponential", "spherical", "gaussian", "linear", "idw")):
+    par = []
+    for t in range(n_dates):
+        m = models[t % len(models)]
+        par.append(dict(use_idw=True) if m == "idw" else
+                   dict(nugget=float(rng.uniform(0.5, 2.0)) * (4.0 if m == "gaussian" else 1.0),   # gaussian: ill-conditioned
+                        sill=float(rng.uniform(10.0, 60.0)),
+                        range=float(rng.uniform(8e3, 40e3)) * (0.3 if m == "gaussian" else 1.0), model=m))
+    return par
+
+
+def _kriging_engine_args(par):
+    model = [0 if p.get("use_idw") else ref.VARIOGRAM_MODELS[p["model"]] for p in par]
+    get = lambda k: [0.0 if p.get("use_idw") else p[k] for p in par]   # noqa: E731
+    rng_ = [1.0 if p.get("use_idw") else p["range"] for p in par]
+    return model, get("nugget"), get("sill"), rng_
+
+
+@pytest.mark.parametrize("shape", [(23, 17, 12, 20), (9, 7, 30, 140), (40, 30, 70, 10), (5, 3, 2, 6)])
+def test_kriging_matches_oracle(shape):
+    """ipr_kriging_f64 (one LU per date + the cell x station variogram pass) against the reference's literal
+    per-cell solve(gamma_matrix, gamma_vector) as restated by the oracle, for the four variogram models, fallback
+    dates, NA, constant / single-station / empty dates.  Tolerance: 1e-9, widened by the conditioning of the
+    date's gamma matrix (the two solve orders agree to kappa * eps; kappa is asserted to stay moderate)."""
+    ncol, nrow, n_st, n_dates = shape
+    rng = np.random.default_rng(n_st)
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(ncol, nrow, n_st, n_dates, na_frac=0.15, seed=n_st + 1)
+    obs = obs + np.where(np.isnan(obs), 0.0, rng.uniform(0.0, 0.5, obs.shape))      # few ties: no constant dates by accident
+    obs[0, :] = np.nan
+    if n_dates > 3:
+        obs[1, :] = np.nan
+        obs[1, 0] = 2.5
+        obs[2, :] = np.where(np.isnan(obs[2, :]), np.nan, 1.25)
+    par = _kriging_params(n_dates, rng)
+    model, nug, sill, rng_ = _kriging_engine_args(par)
+    got = engine.kriging_grid(cx, cy, sx, sy, obs, model, nug, sill, rng_)
+    want = ref.kriging_reference(cx, cy, sx, sy, obs, par)
+    assert not np.isnan(got).any() and np.all(got >= 0.0)
+    assert np.all(got[:, 0] == 0.0)
+    if n_dates > 3:
+        assert np.all(got[:, 1] == 2.5) and np.all(got[:, 2] == 1.25)
+    dss = ref.distance_matrix(sx, sy, sx, sy)
+    n_ill = 0
+    for t in range(n_dates):
+        tol = 1e-9
+        p = par[t]
+        ok = ~np.isnan(obs[t])
+        if not p.get("use_idw") and ok.sum() >= 2:
+            n = int(ok.sum())
+            gm = np.full((n + 1, n + 1), p["nugget"])
+            off = ~np.eye(n, dtype=bool)
+            gm[:n, :n][off] = ref.variogram_models(dss[np.ix_(ok, ok)], p["nugget"], p["sill"], p["range"], p["model"])[off]
+            gm[n, :n] = gm[:n, n] = 1.0
+            gm[n, n] = 0.0
+            kappa = np.linalg.cond(gm)
+            if kappa > 1e9:      # near the reference's own kappa > 1e12 fallback: the two solve orders are not comparable
+                n_ill += 1
+                continue
+            tol = max(1e-9, 100 * kappa * 2.0 ** -53)
+        # absolute floor on the scale of the observations: max(0, .) clips values that cancel to ~0
+        scale = np.nanmax(np.abs(obs[t])) if ok.any() else 1.0
+        assert np.all(np.abs(got[:, t] - want[:, t]) <= tol * np.maximum(np.abs(want[:, t]), scale)), (t, par[t])
+    assert n_ill <= n_dates // 4, "most dates must be well enough conditioned to be compared"
+
+
+def test_kriging_singular_system_takes_the_mean_and_shards_agree():
+    """Two stations at the same place make gamma_matrix exactly singular: solve() raises in the reference and the
+    layer is mean(available_values) (R/Kriging_Ordinary.R:494).  Also: the cell-split scheduler on the kriging path."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(12, 9, 8, 4, seed=3)
+    obs = obs + 0.1 * np.arange(obs.shape[1])[None, :] + 0.3
+    sx[5], sy[5] = sx[2], sy[2]                                        # duplicate location -> two equal rows
+    par = [dict(nugget=1.0, sill=20.0, range=15e3, model="exponential")] * 4
+    model, nug, sill, rng_ = _kriging_engine_args(par)
+    one = engine.kriging_grid(cx, cy, sx, sy, obs, model, nug, sill, rng_, devices=[0])
+    for t in range(4):
+        assert np.allclose(one[:, t], obs[t].mean(), rtol=1e-13, atol=0)
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(30, 21, 25, 150, na_frac=0.1, seed=4)
+    rng = np.random.default_rng(1)
+    par = _kriging_params(150, rng)
+    model, nug, sill, rng_ = _kriging_engine_args(par)
+    one = engine.kriging_grid(cx, cy, sx, sy, obs, model, nug, sill, rng_, devices=[0])
+    many = engine.kriging_grid(cx, cy, sx, sy, obs, model, nug, sill, rng_, devices=[0, 0, 0])
+    assert np.array_equal(one, many)          # the solve does not depend on the cell range; the pass is per cell

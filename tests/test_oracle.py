@@ -270,3 +270,37 @@ def test_kriging_fallback_oracle_rules(seed):
         if ok[s]:
             c = int(np.flatnonzero((cx == sx[s]) & (cy == sy[s]))[0])
             assert abs(got[c, t] - obs[t, s]) <= 1e-12 * max(abs(obs[t, s]), 1.0)
+
+
+def test_kriging_oracle_literal_solve_equals_one_solve_per_date():
+    """The kriging branch of perform_kriging (R/Kriging_Ordinary.R:428-497), literal per-cell solve, against the
+    identity the engine uses — sum(w v) = alpha' [gamma(c); 1] with alpha = Gamma^-1 [v; 0] — and against the
+    interpolation property of kriging with a zero nugget effect on the diagonal... which the reference does NOT
+    have: its diagonal holds the nugget, so a cell on a station does not reproduce the observation exactly."""
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(8, 6, 9, 5, na_frac=0.2, plant_zero_dist=1, seed=11)
+    obs[0, :] = np.where(np.isnan(obs[0, :]), np.nan, 3.0)            # constant date
+    params = [dict(nugget=0.4, sill=30.0, range=9000.0, model=m) for m in ("exponential", "spherical", "gaussian", "linear")]
+    params.append(dict(use_idw=True))
+    got = ref.kriging_reference(cx, cy, sx, sy, obs, params)
+    assert np.all(got[:, 0] == 3.0) and not np.isnan(got).any() and np.all(got >= 0.0)
+    assert_parity(got[:, 4], ref.kriging_idw_fallback_one_date(ref.distance_matrix(cx, cy, sx, sy), obs[4]), label="use_idw")
+    dist = ref.distance_matrix(cx, cy, sx, sy)
+    dss = ref.distance_matrix(sx, sy, sx, sy)
+    for t in (1, 2, 3):
+        ok = ~np.isnan(obs[t])
+        v = obs[t][ok]
+        if v.size < 2 or np.unique(v).size == 1:
+            continue
+        n = v.size
+        p = params[t]
+        gm = np.full((n + 1, n + 1), p["nugget"])
+        h = dss[np.ix_(ok, ok)]
+        off = ~np.eye(n, dtype=bool)
+        gm[:n, :n][off] = ref.variogram_models(h, p["nugget"], p["sill"], p["range"], p["model"])[off]
+        gm[n, :n] = gm[:n, n] = 1.0
+        gm[n, n] = 0.0
+        alpha = np.linalg.solve(gm, np.append(v, 0.0))
+        g = ref.variogram_models(dist[:, ok], p["nugget"], p["sill"], p["range"], p["model"])
+        want = np.maximum(0.0, g @ alpha[:n] + alpha[n])
+        kappa = np.linalg.cond(gm)
+        assert np.allclose(got[:, t], want, rtol=max(1e-10, 50 * kappa * 2.0 ** -53), atol=1e-12)
