@@ -1576,7 +1576,8 @@ struct KrigingArgs {
     double* fallback_value;      // per list entry: mean of the available values (solve() failed, :494)
 };
 
-constexpr int kKrigThreads = 512;
+constexpr int kKrigThreads = 1024;
+constexpr int kKrigLChunk = 4096;   // multipliers of one elimination step staged in shared memory (32 KB)
 
 __global__ void __launch_bounds__(kKrigThreads) kriging_solve_kernel(const KrigingArgs a) {
     __shared__ int s_n;
@@ -1585,6 +1586,7 @@ __global__ void __launch_bounds__(kKrigThreads) kriging_solve_kernel(const Krigi
     __shared__ int s_red_i[kKrigThreads / 32];
     __shared__ int s_piv;
     __shared__ double s_pivval;
+    __shared__ double s_l[kKrigLChunk];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = a.n_st + 1;
     double* G = a.scratch + (size_t)blockIdx.x * ld * (ld + 1);
@@ -1698,15 +1700,32 @@ __global__ void __launch_bounds__(kKrigThreads) kriging_solve_kernel(const Krigi
             // exactly 1, x * (1 / x) need not be — two coincident stations must leave an exactly zero row behind,
             // which is how the reference's solve() detects the singular system
             const double piv = G[(size_t)k * ld + k];
-            for (int i = k + 1 + tid; i < m1; i += kKrigThreads) G[(size_t)k * ld + i] /= piv;
-            __syncthreads();
-            // trailing update, columns k+1 .. m1 (the last one is b): coalesced down the rows
             const int rows = m1 - k - 1;
-            if (rows > 0) {
-                const long long work = (long long)rows * (m1 - k);
-                for (long long e = tid; e < work; e += kKrigThreads) {
-                    const int i = k + 1 + (int)(e % rows), j = k + 1 + (int)(e / rows);
-                    G[(size_t)j * ld + i] = fma(-G[(size_t)k * ld + i], G[(size_t)j * ld + k], G[(size_t)j * ld + i]);
+            // the multipliers go to shared memory in chunks (a column of up to n + 1 entries need not fit at once)
+            for (int r0 = 0; r0 < rows; r0 += kKrigLChunk) {
+                const int nr = min(kKrigLChunk, rows - r0);
+                __syncthreads();
+                for (int i = tid; i < nr; i += kKrigThreads) {
+                    const double l = G[(size_t)k * ld + k + 1 + r0 + i] / piv;
+                    G[(size_t)k * ld + k + 1 + r0 + i] = l;
+                    s_l[i] = l;
+                }
+                __syncthreads();
+                // trailing update of rows [k+1+r0, +nr), columns k+1 .. m1 (the last one is b): a warp per column,
+                // lanes down the rows (coalesced), no index arithmetic beyond adds
+                for (int j = k + 1 + warp; j <= m1; j += kKrigThreads / 32) {
+                    double* col = G + (size_t)j * ld;
+                    const double ukj = col[k];
+                    double* dst = col + k + 1 + r0;
+                    int i = lane;
+                    for (; i + 96 < nr; i += 128) {           // four independent loads in flight per lane
+                        const double d0 = dst[i], d1 = dst[i + 32], d2 = dst[i + 64], d3 = dst[i + 96];
+                        dst[i] = fma(-s_l[i], ukj, d0);
+                        dst[i + 32] = fma(-s_l[i + 32], ukj, d1);
+                        dst[i + 64] = fma(-s_l[i + 64], ukj, d2);
+                        dst[i + 96] = fma(-s_l[i + 96], ukj, d3);
+                    }
+                    for (; i < nr; i += 32) dst[i] = fma(-s_l[i], ukj, dst[i]);
                 }
             }
             __syncthreads();

@@ -123,5 +123,22 @@
         as.double(Points_Train$X), as.double(Points_Train$Y), obs, .ipr_devices(devices), NULL, FALSE)
 }
 
+# --- SURVEY 8(f3): the kriging branch ---------------------------------------------------------------
+# Replaces the prediction step of perform_kriging() for ALL dates at once.  process_day() keeps what it does
+# before it (R/Kriging_Ordinary.R:510-540: the empirical variogram and fit_variogram per date) and the decision of
+# :428-462 (flat variogram, det == 0, kappa > 1e12 -> IDW); it then only RECORDS the outcome per date:
+#   params: data.frame(model = <0 fallback | 1 exponential | 2 spherical | 3 gaussian | 4 linear>, nugget, sill, range)
+# and the layers of all dates come from one call.  `obs`: n_dates x n_stations (NA = not available that day), columns
+# aligned with Points_Train.  Returns the n_cells x n_dates matrix of layer values in data_Kriging order: the
+# constant layers of the prelude (:406-423), the IDW fallback (:465-476) and max(0, sum(weights * values))
+# (:478-497; mean(values) where the system is exactly singular, :494).
+.ipr_kriging_core <- function(data_Kriging, Points_Train, obs, params,
+                              devices = getOption("InterpolateR.devices", NULL)) {
+  storage.mode(obs) <- "double"
+  .Call(C_ipr_kriging, as.double(data_Kriging$X), as.double(data_Kriging$Y),
+        as.double(Points_Train$X), as.double(Points_Train$Y), obs, as.integer(params$model),
+        as.double(params$nugget), as.double(params$sill), as.double(params$range), .ipr_devices(devices))
+}
+
 # returns the device memory the engine keeps between calls (call it after a large job if other GPU work follows)
 ipr_release <- function() invisible(.Call(C_ipr_release))

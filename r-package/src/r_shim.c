@@ -8,6 +8,7 @@
  *   C_ipr_idw(cell_x, cell_y, st_x, st_y, obs, p, devices, progress, pinned)            n_cells x n_dates
  *   C_ipr_cressman(cell_x, cell_y, st_x, st_y, obs, radii_m, devices, progress, pinned) n_cells x n_dates x n_radii
  *   C_ipr_idw_kriging(cell_x, cell_y, st_x, st_y, obs, devices, progress, pinned)       n_cells x n_dates
+ *   C_ipr_kriging(cell_x, cell_y, st_x, st_y, obs, model, nugget, sill, range, devices)  n_cells x n_dates
  *   C_ipr_release()                                                                      NULL
  *
  * obs is the n_dates x n_stations double matrix (column-major, NA = missing) whose columns are aligned with
@@ -174,6 +175,26 @@ SEXP C_ipr_idw_kriging(SEXP cell_x, SEXP cell_y, SEXP st_x, SEXP st_y, SEXP obs,
     return out;
 }
 
+/* ordinary kriging: model (integer, 0 = IDW fallback, 1..4 = exponential / spherical / gaussian / linear) and the
+ * fitted nugget / sill / range, one entry per date (row of obs) */
+SEXP C_ipr_kriging(SEXP cell_x, SEXP cell_y, SEXP st_x, SEXP st_y, SEXP obs, SEXP model, SEXP nugget, SEXP sill,
+                   SEXP range, SEXP devices) {
+    const common_args a = check_common(cell_x, cell_y, st_x, st_y, obs, devices, R_NilValue);
+    check_real(nugget, "nugget"); check_real(sill, "sill"); check_real(range, "range");
+    if (!isInteger(model)) error("model must be an integer vector (0 = IDW fallback, 1..4 = variogram model)");
+    if (LENGTH(model) != a.n_dates || LENGTH(nugget) != a.n_dates || LENGTH(sill) != a.n_dates ||
+        LENGTH(range) != a.n_dates)
+        error("model, nugget, sill and range need one entry per date (row of obs)");
+    SEXP out = PROTECT(alloc_result(a.n_cells, a.n_dates, 1, 0, 0));
+    char err[512] = "";
+    const int rc = ipr_kriging_f64(REAL(cell_x), REAL(cell_y), (int64_t)a.n_cells, REAL(st_x), REAL(st_y), a.n_st,
+                                   REAL(obs), a.n_dates, INTEGER(model), REAL(nugget), REAL(sill), REAL(range), a.dev,
+                                   a.n_dev, REAL(out), err, sizeof err);
+    UNPROTECT(1);
+    raise_job_error(rc, 0, 0, err);
+    return out;
+}
+
 SEXP C_ipr_cressman(SEXP cell_x, SEXP cell_y, SEXP st_x, SEXP st_y, SEXP obs, SEXP radii_m, SEXP devices,
                     SEXP progress, SEXP pinned) {
     const common_args a = check_common(cell_x, cell_y, st_x, st_y, obs, devices, progress);
@@ -202,6 +223,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_ipr_idw", (DL_FUNC)&C_ipr_idw, 9},
     {"C_ipr_cressman", (DL_FUNC)&C_ipr_cressman, 9},
     {"C_ipr_idw_kriging", (DL_FUNC)&C_ipr_idw_kriging, 8},
+    {"C_ipr_kriging", (DL_FUNC)&C_ipr_kriging, 10},
     {"C_ipr_release", (DL_FUNC)&C_ipr_release, 0},
     {NULL, NULL, 0}};
 

@@ -3,8 +3,9 @@
  *
  *   shim_driver <in.bin> <out.bin>
  *
- * in.bin  : int64 header {mode (0 IDW, 1 Cressman, 2 Kriging IDW fallback), n_cells, n_st, n_dates, n_radii},
- *           then doubles: cell_x, cell_y, st_x, st_y, obs (column-major n_dates x n_st), p | radii_m | (nothing)
+ * in.bin  : int64 header {mode (0 IDW, 1 Cressman, 2 Kriging IDW fallback, 3 ordinary kriging), n_cells, n_st,
+ *           n_dates, n_radii}, then doubles: cell_x, cell_y, st_x, st_y, obs (column-major n_dates x n_st),
+ *           p | radii_m | (nothing) | model codes, nugget, sill, range (n_dates each)
  * out.bin : the doubles of the returned array.
  * environment: MOCK_PINNED=1            pinned = TRUE (result through the R_allocator_t of the shim)
  *              MOCK_PROGRESS=1          pass a progress closure; its calls are logged on stderr
@@ -191,6 +192,7 @@ void R_init_InterpolateR(DllInfo* dll);
 void R_unload_InterpolateR(DllInfo* dll);
 typedef SEXP (*call9)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 typedef SEXP (*call8)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*call10)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 typedef SEXP (*call0)(void);
 
 static SEXP read_real(FILE* f, R_xlen_t n) {
@@ -233,7 +235,16 @@ int main(int argc, char** argv) {
     obs->nrow = n_dates;
     obs->ncol = n_st;
     obs->ndim = 2;
-    SEXP last = mode == 2 ? R_NilValue : read_real(f, mode == 0 ? 1 : n_radii);
+    SEXP last = (mode == 2 || mode == 3) ? R_NilValue : read_real(f, mode == 0 ? 1 : n_radii);
+    SEXP k_model = R_NilValue, k_nug = R_NilValue, k_sill = R_NilValue, k_range = R_NilValue;
+    if (mode == 3) {
+        SEXP codes = read_real(f, n_dates);
+        k_model = new_vec(INTSXP, n_dates);
+        for (int i = 0; i < n_dates; i++) INTEGER(k_model)[i] = (int)REAL(codes)[i];
+        k_nug = read_real(f, n_dates);
+        k_sill = read_real(f, n_dates);
+        k_range = read_real(f, n_dates);
+    }
     fclose(f);
     SEXP pinned = new_vec(LGLSXP, 1);
     INTEGER(pinned)[0] = env_int("MOCK_PINNED", 0);
@@ -251,7 +262,10 @@ int main(int argc, char** argv) {
         code = 3;
     } else {
         /* .Call(...) */
-        if (mode == 2)
+        if (mode == 3)
+            out = ((call10)lookup("C_ipr_kriging", 10))(cell_x, cell_y, st_x, st_y, obs, k_model, k_nug, k_sill, k_range,
+                                                        R_NilValue);
+        else if (mode == 2)
             out = ((call8)lookup("C_ipr_idw_kriging", 8))(cell_x, cell_y, st_x, st_y, obs, R_NilValue, progress, pinned);
         else
             out = ((call9)lookup(mode == 0 ? "C_ipr_idw" : "C_ipr_cressman", 9))(cell_x, cell_y, st_x, st_y, obs, last,
@@ -268,7 +282,7 @@ int main(int argc, char** argv) {
             fprintf(stderr, "unexpected result shape\n");
             return 4;
         }
-        if (env_int("MOCK_PINNED", 0) && pinned_allocs != 1) {
+        if (env_int("MOCK_PINNED", 0) && mode != 3 && pinned_allocs != 1) {
             fprintf(stderr, "pinned = TRUE did not go through the allocator\n");
             return 4;
         }

@@ -59,7 +59,7 @@ def test_shim_raises_an_r_error_without_a_device(driver, tmp_path):
     if _has_gpu():
         pytest.skip("a device is present: covered by the GPU test")
     case = synthetic.synthetic_case(6, 5, 7, 9, na_frac=0.1)
-    for mode, last in ((0, [2.0]), (1, [5e3, 2e4]), (2, [])):
+    for mode, last in ((0, [2.0]), (1, [5e3, 2e4]), (2, []), (3, [1.0] * 9 + [1.0] * 9 + [20.0] * 9 + [9e3] * 9)):
         res, out = _run(driver, tmp_path, mode, case, last, MOCK_PROGRESS=1)
         assert res.returncode == 3, (res.returncode, res.stderr)      # error() was raised, nothing crashed
         assert out is None and "R error: interpolater_b200 (code -" in res.stderr
@@ -95,6 +95,18 @@ def test_shim_end_to_end_matches_oracle(driver, tmp_path):
     assert res.returncode == 0, res.stderr
     assert_parity(out.reshape(obs.shape[0], cx.size).T, ref.kriging_idw_fallback_reference(cx, cy, sx, sy, obs),
                   label="Kriging IDW fallback through the .Call shim")
+    # ordinary kriging: model codes + fitted parameters per date (a third of the dates fall back to IDW)
+    kc = synthetic.synthetic_case(19, 13, 14, 30, na_frac=0.1, seed=78)
+    D = kc[4].shape[0]
+    par = [dict(use_idw=True) if t % 3 == 0 else dict(nugget=1.0 + 0.01 * t, sill=25.0, range=12e3, model=("exponential", "spherical")[t % 2])
+           for t in range(D)]
+    codes = [0.0 if p.get("use_idw") else float(ref.VARIOGRAM_MODELS[p["model"]]) for p in par]
+    extra = codes + [p.get("nugget", 0.0) for p in par] + [p.get("sill", 0.0) for p in par] + [p.get("range", 1.0) for p in par]
+    res, out = _run(driver, tmp_path, 3, kc, extra)
+    assert res.returncode == 0, res.stderr
+    want = ref.kriging_reference(kc[0], kc[1], kc[2], kc[3], kc[4], par)
+    got = out.reshape(D, kc[0].size).T
+    assert np.all(np.abs(got - want) <= 1e-8 * np.maximum(np.abs(want), np.nanmax(kc[4])))
 
 
 @pytest.mark.gpu

@@ -23,7 +23,8 @@ def test_r_shim_compiles_against_mock_r_api():
 def test_r_helper_calls_registered_routines():
     shim = open(os.path.join(ROOT, "r-package", "src", "r_shim.c")).read()
     registered = dict(re.findall(r'\{"(C_ipr_\w+)",\s*\(DL_FUNC\)&\w+,\s*(\d+)\}', shim))
-    assert registered == {"C_ipr_idw": "9", "C_ipr_cressman": "9", "C_ipr_idw_kriging": "8", "C_ipr_release": "0"}
+    assert registered == {"C_ipr_idw": "9", "C_ipr_cressman": "9", "C_ipr_idw_kriging": "8", "C_ipr_kriging": "10",
+                          "C_ipr_release": "0"}
     helper = open(os.path.join(ROOT, "r-package", "R", "ipr_core.R")).read()
     helper_code = "\n".join(l.split("#")[0] for l in helper.splitlines())
     calls = re.findall(r"\.Call\((C_ipr_\w+)((?:[^()]|\((?:[^()]|\([^()]*\))*\))*)\)", helper_code)
