@@ -308,8 +308,12 @@ class Ctx:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
         torch.cuda.set_device(self.local_rank)
+        self.cpu_group = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            # a CPU-side group: ranks that must WAIT while rank 0 drives every GPU from one process block on a
+            # socket, not inside an NCCL kernel spinning on their GPU (which would time-slice with rank 0's work)
+            self.cpu_group = dist.new_group(backend="gloo")
         self.lib = _native.load()
         with open(os.path.join(ROOT, "profiles", "fp64_peaks.json")) as f:
             self.peaks = json.load(f)
@@ -332,6 +336,10 @@ class Ctx:
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def cpu_barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
 
     def max_over_ranks(self, x):
         if self.world == 1:
@@ -627,7 +635,7 @@ def run_workload(a, wl, ctx):
         # ---- N > 1: ONE process driving every GPU through the device list of the same call ----
         if a.inproc_steps > 0 and world > 1 and not weak and wl == "idw":
             full_bytes = n_stacks * total_cells * D * 8
-            ctx.barrier()
+            ctx.barrier()      # every GPU idle; the other ranks then wait on the CPU-side group
             if rank == 0:
                 hp = ctx.pinned(full_bytes)
                 ips = []
@@ -643,6 +651,7 @@ def run_workload(a, wl, ctx):
                     "api": "ipr_idw_f64(devices = 0..%d) from ONE process: a host thread + plan per GPU, every GPU "
                            "writes its column range of the caller's pinned matrix" % (world - 1),
                 }
+            ctx.cpu_barrier()
             ctx.barrier()
         lib.ipr_host_free(obs_pin_ptr)
 

@@ -54,7 +54,7 @@ cx, cy, sx, sy, obs = synthetic.synthetic_case(1000, 1000, 2000, D)
 obs_f = np.asfortranarray(obs)
 out = host.numpy().T          # (C, D) Fortran-ordered view of the pinned matrix
 # IPR_D2H_ROWS is read once per process: the row-wise variant is run by re-executing this script with the switch set
-mode = os.environ.get("IPR_D2H_ROWS", "0")
+mode = os.environ.get("IPR_D2H_ROWS", "1 (default)")
 for i in range(4):
     t = time.perf_counter()
     engine.idw_grid(cx, cy, sx, sy, obs_f, out=out, devices=list(range(n)))
