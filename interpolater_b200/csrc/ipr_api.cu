@@ -810,8 +810,10 @@ int run_cressman_radius(ipr_plan* p, double radius_m, int t0, int t1, double* d_
     c.list_cap = list_cap;
     c.active_total = p->d_active_total;
     c.tile_counter = p->d_cr_counter;
+    // per-phase cycle counters of the kernel: only in a build with -DIPR_CR_PROFILE=1 (they cost 16 registers);
+    // single device, single thread — a debugging aid, not part of the product path
     static unsigned long long* d_prof = nullptr;
-    if (getenv("IPR_CR_PROF")) {
+    if (IPR_CR_PROFILE && getenv("IPR_CR_PROF")) {
         if (!d_prof) IPR_CUDA(cudaMalloc(&d_prof, 64));
         IPR_CUDA(cudaMemsetAsync(d_prof, 0, 64, p->stream));
         c.prof = d_prof;
