@@ -117,6 +117,26 @@ def test_cressman_every_cell_tile_shape_matches_oracle(monkeypatch, xdiv):
         assert_parity(got[i], want[i], label=f"cressman xdiv={xdiv} R={radii[i]:.0f}")
 
 
+@pytest.mark.parametrize("xdiv", ["1", "4", "16", "64"])
+@pytest.mark.parametrize("grid", [(40, 27), (64, 16), (8, 9)])
+def test_cressman_rectangular_tiles_on_rasters_with_ragged_edges(monkeypatch, xdiv, grid):
+    """Rasters whose rows are whole numbers of 8-cell runs get exact rectangular tiles (regular_run_perm): 5, 8
+    or 1 runs per row against tile widths of 1 / 2 / 4 / 8 runs and row counts that are no multiple of the tile
+    height, so that full tiles, ragged right / bottom edges and the padding runs all occur."""
+    ncol, nrow = grid
+    cx, cy, sx, sy, obs = synthetic.synthetic_case(ncol, nrow, 90, 140, na_frac=0.05, seed=ncol + int(xdiv))
+    radii = ref.cressman_radii_m([3, 12, 60])
+    want = ref.cressman_reference(cx, cy, sx, sy, obs, radii)
+    monkeypatch.setenv("IPR_CR_XDIV", xdiv)
+    got = engine.cressman_grid(cx, cy, sx, sy, obs, radii)
+    for i in range(len(radii)):
+        assert_parity(got[i], want[i], label=f"raster {grid} xdiv={xdiv} R={radii[i]:.0f}")
+    monkeypatch.setenv("IPR_CR_MORTON", "1")          # the general (Morton) tiles on the same raster
+    got_m = engine.cressman_grid(cx, cy, sx, sy, obs, radii)
+    for i in range(len(radii)):
+        assert_parity(got_m[i], want[i], label=f"raster {grid} Morton xdiv={xdiv} R={radii[i]:.0f}")
+
+
 def test_cressman_weights_at_the_cut_off_are_the_references():
     """A station exactly R away from a cell centre (d == R: weight 0/(2 R^2) = 0, still 'in range' for the
     denominator test) and stations a rounding error inside / outside the radius: the fused kernel computes
