@@ -1577,7 +1577,7 @@ struct KrigingArgs {
 };
 
 constexpr int kKrigThreads = 1024;
-constexpr int kKrigLChunk = 4096;   // multipliers of one elimination step staged in shared memory (32 KB)
+constexpr int kKrigNB = 16;         // panel width of the blocked elimination
 
 __global__ void __launch_bounds__(kKrigThreads) kriging_solve_kernel(const KrigingArgs a) {
     __shared__ int s_n;
@@ -1586,7 +1586,8 @@ __global__ void __launch_bounds__(kKrigThreads) kriging_solve_kernel(const Krigi
     __shared__ int s_red_i[kKrigThreads / 32];
     __shared__ int s_piv;
     __shared__ double s_pivval;
-    __shared__ double s_l[kKrigLChunk];
+    __shared__ double s_lt[kKrigNB * 128];   // L21 tile [p][row]
+    __shared__ double s_ut[kKrigNB * 64];    // U12 tile [p][col]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = a.n_st + 1;
     double* G = a.scratch + (size_t)blockIdx.x * ld * (ld + 1);
@@ -1646,88 +1647,130 @@ __global__ void __launch_bounds__(kKrigThreads) kriging_solve_kernel(const Krigi
             G[(size_t)j * ld + i] = g;
         }
         __syncthreads();
-        // ---- Gaussian elimination with partial pivoting on the augmented matrix ----
+        // ---- blocked Gaussian elimination with partial pivoting on the augmented matrix (right-looking, panels of
+        //      kKrigNB columns).  Every entry outside the panel is updated by ONE ascending chain of FMAs starting
+        //      from the entry itself — in the row-block solve (U12) and in the trailing update alike — so two
+        //      identical rows (coincident stations) go through bit-identical operations and leave an exactly zero
+        //      row behind, which is how the reference's solve() detects the singular system ----
         bool singular = false;
-        for (int k = 0; k < m1; k++) {
-            double best = -1.0;
-            int bi = k;
-            for (int i = k + tid; i < m1; i += kKrigThreads) {
-                const double v = fabs(G[(size_t)k * ld + i]);
-                if (v > best) {
-                    best = v;
-                    bi = i;
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) {
-                    best = ov;
-                    bi = oi;
-                }
-            }
-            if (lane == 0) {
-                s_red_v[warp] = best;
-                s_red_i[warp] = bi;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                double bv = s_red_v[0];
-                int bb = s_red_i[0];
-                for (int w = 1; w < kKrigThreads / 32; w++)
-                    if (s_red_v[w] > bv || (s_red_v[w] == bv && s_red_i[w] < bb)) {
-                        bv = s_red_v[w];
-                        bb = s_red_i[w];
+        const int ncols = m1 + 1;                    // columns of [Gamma | b]
+        for (int k0 = 0; k0 < m1 && !singular; k0 += kKrigNB) {
+            const int nb = min(kKrigNB, m1 - k0);
+            // 1. panel: columns k0 .. k0+nb-1, updates confined to the panel, row swaps over all remaining columns
+            for (int k = k0; k < k0 + nb; k++) {
+                double best = -1.0;
+                int bi = k;
+                for (int i = k + tid; i < m1; i += kKrigThreads) {
+                    const double v = fabs(G[(size_t)k * ld + i]);
+                    if (v > best) {
+                        best = v;
+                        bi = i;
                     }
-                s_piv = bb;
-                s_pivval = bv;
-            }
-            __syncthreads();
-            if (!(s_pivval > 0.0)) {                 // exactly singular: solve() raises, the reference takes the mean
-                singular = true;
-                break;
-            }
-            const int pr = s_piv;
-            if (pr != k)
-                for (int j = k + tid; j <= m1; j += kKrigThreads) {
-                    const double x = G[(size_t)j * ld + k];
-                    G[(size_t)j * ld + k] = G[(size_t)j * ld + pr];
-                    G[(size_t)j * ld + pr] = x;
                 }
-            __syncthreads();
-            // multipliers by true division, as LAPACK's dgetf2 scales a column whose pivot is not tiny: x / x is
-            // exactly 1, x * (1 / x) need not be — two coincident stations must leave an exactly zero row behind,
-            // which is how the reference's solve() detects the singular system
-            const double piv = G[(size_t)k * ld + k];
-            const int rows = m1 - k - 1;
-            // the multipliers go to shared memory in chunks (a column of up to n + 1 entries need not fit at once)
-            for (int r0 = 0; r0 < rows; r0 += kKrigLChunk) {
-                const int nr = min(kKrigLChunk, rows - r0);
-                __syncthreads();
-                for (int i = tid; i < nr; i += kKrigThreads) {
-                    const double l = G[(size_t)k * ld + k + 1 + r0 + i] / piv;
-                    G[(size_t)k * ld + k + 1 + r0 + i] = l;
-                    s_l[i] = l;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) {
+                        best = ov;
+                        bi = oi;
+                    }
+                }
+                if (lane == 0) {
+                    s_red_v[warp] = best;
+                    s_red_i[warp] = bi;
                 }
                 __syncthreads();
-                // trailing update of rows [k+1+r0, +nr), columns k+1 .. m1 (the last one is b): a warp per column,
-                // lanes down the rows (coalesced), no index arithmetic beyond adds
-                for (int j = k + 1 + warp; j <= m1; j += kKrigThreads / 32) {
+                if (tid == 0) {
+                    double bv = s_red_v[0];
+                    int bb = s_red_i[0];
+                    for (int w = 1; w < kKrigThreads / 32; w++)
+                        if (s_red_v[w] > bv || (s_red_v[w] == bv && s_red_i[w] < bb)) {
+                            bv = s_red_v[w];
+                            bb = s_red_i[w];
+                        }
+                    s_piv = bb;
+                    s_pivval = bv;
+                }
+                __syncthreads();
+                if (!(s_pivval > 0.0)) {             // exactly singular: solve() raises, the reference takes the mean
+                    singular = true;
+                    break;
+                }
+                const int pr = s_piv;
+                if (pr != k)
+                    for (int j = k0 + tid; j < ncols; j += kKrigThreads) {
+                        const double x = G[(size_t)j * ld + k];
+                        G[(size_t)j * ld + k] = G[(size_t)j * ld + pr];
+                        G[(size_t)j * ld + pr] = x;
+                    }
+                __syncthreads();
+                // multipliers by true division (LAPACK's dgetf2): x / x is exactly 1, x * (1 / x) need not be
+                const double piv = G[(size_t)k * ld + k];
+                for (int i = k + 1 + tid; i < m1; i += kKrigThreads) G[(size_t)k * ld + i] /= piv;
+                __syncthreads();
+                // the rest of the panel: a warp per column, lanes down the rows
+                for (int j = k + 1 + warp; j < k0 + nb; j += kKrigThreads / 32) {
                     double* col = G + (size_t)j * ld;
                     const double ukj = col[k];
-                    double* dst = col + k + 1 + r0;
-                    int i = lane;
-                    for (; i + 96 < nr; i += 128) {           // four independent loads in flight per lane
-                        const double d0 = dst[i], d1 = dst[i + 32], d2 = dst[i + 64], d3 = dst[i + 96];
-                        dst[i] = fma(-s_l[i], ukj, d0);
-                        dst[i + 32] = fma(-s_l[i + 32], ukj, d1);
-                        dst[i + 64] = fma(-s_l[i + 64], ukj, d2);
-                        dst[i + 96] = fma(-s_l[i + 96], ukj, d3);
-                    }
-                    for (; i < nr; i += 32) dst[i] = fma(-s_l[i], ukj, dst[i]);
+                    const double* lcol = G + (size_t)k * ld;
+                    for (int i = k + 1 + lane; i < m1; i += 32) col[i] = fma(-lcol[i], ukj, col[i]);
+                }
+                __syncthreads();
+            }
+            if (singular) break;
+            const int c0 = k0 + nb;                  // first column / row beyond the panel
+            if (c0 >= ncols) break;
+            // 2. row block: U12 = L11^-1 A12 (unit lower triangular), one thread per column, ascending chains
+            for (int j = c0 + tid; j < ncols; j += kKrigThreads) {
+                double* col = G + (size_t)j * ld;
+                for (int qq = 1; qq < nb; qq++) {
+                    double val = col[k0 + qq];
+                    for (int pp = 0; pp < qq; pp++) val = fma(-G[(size_t)(k0 + pp) * ld + k0 + qq], col[k0 + pp], val);
+                    col[k0 + qq] = val;
                 }
             }
+            __syncthreads();
+            // 3. trailing update A22 -= L21 U12 in 128-row x 64-column tiles: L21 and U12 tiles in shared memory,
+            //    a thread owns rows tx, tx + 64 and four columns; the chain over the panel is ascending per entry
+            const int tx = tid & 63, ty = tid >> 6;  // 64 x 16
+            for (int r0 = c0; r0 < m1; r0 += 128)
+                for (int j0 = c0; j0 < ncols; j0 += 64) {
+                    __syncthreads();
+                    for (int e = tid; e < nb * 128; e += kKrigThreads) {        // Ls[p][row]
+                        const int pp = e >> 7, rr = e & 127;
+                        s_lt[e] = (r0 + rr < m1) ? G[(size_t)(k0 + pp) * ld + r0 + rr] : 0.0;
+                    }
+                    for (int e = tid; e < nb * 64; e += kKrigThreads) {         // Us[p][col]
+                        const int cc = e / nb, pp = e - cc * nb;                // consecutive threads walk down a column
+                        s_ut[pp * 64 + cc] = (j0 + cc < ncols) ? G[(size_t)(j0 + cc) * ld + k0 + pp] : 0.0;
+                    }
+                    __syncthreads();
+                    double v[2][4];
+#pragma unroll
+                    for (int a2 = 0; a2 < 2; a2++)
+#pragma unroll
+                        for (int b4 = 0; b4 < 4; b4++) {
+                            const int i = r0 + tx + 64 * a2, j = j0 + 4 * ty + b4;
+                            v[a2][b4] = (i < m1 && j < ncols) ? G[(size_t)j * ld + i] : 0.0;
+                        }
+                    for (int pp = 0; pp < nb; pp++) {
+                        const double l0 = s_lt[pp * 128 + tx], l1 = s_lt[pp * 128 + tx + 64];
+#pragma unroll
+                        for (int b4 = 0; b4 < 4; b4++) {
+                            const double u = s_ut[pp * 64 + 4 * ty + b4];
+                            v[0][b4] = fma(-l0, u, v[0][b4]);
+                            v[1][b4] = fma(-l1, u, v[1][b4]);
+                        }
+                    }
+#pragma unroll
+                    for (int a2 = 0; a2 < 2; a2++)
+#pragma unroll
+                        for (int b4 = 0; b4 < 4; b4++) {
+                            const int i = r0 + tx + 64 * a2, j = j0 + 4 * ty + b4;
+                            if (i < m1 && j < ncols) G[(size_t)j * ld + i] = v[a2][b4];
+                        }
+                }
             __syncthreads();
         }
         if (singular) {
